@@ -1,0 +1,135 @@
+/* vrm_b200.h -- C ABI of the B200-native voxel raymarcher hot path (libvrm_b200.so).
+ *
+ * Drop-in boundary for ONE path of lukeduball/VoxelRaymarcher: construction of the two voxel storage
+ * structures + primary-ray generation + both traversal algorithms fused with lookup, shadow ray and lighting.
+ * Everything behind this header is hand-written CUDA for sm_100a; there is no CPU fallback: every entry point
+ * that needs the GPU returns VRM_ERR_CUDA when no device is usable.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/VoxelRaymarcher/src):
+ *   vrm_scene_add_voxels      <- VoxelSceneCPU::insertVoxel               geometry/VoxelSceneCPU.cuh:16-46
+ *   vrm_scene_build           <- VoxelSceneCPU::generateVoxelScene        geometry/VoxelSceneCPU.cuh:49-93
+ *                                + CuckooHashTable ctor                   storage/CuckooHashTable.cuh:20-49,97-178
+ *                                + VoxelClusterStore ctor                 storage/VoxelClusterStore.cuh:37-85
+ *                                + generateVoxelScene<<<1,1>>>            renderer/Renderer.cuh:1066-1086
+ *   vrm_scene_info            <- getArrayDiameter/getArraySize/getMinCoord geometry/VoxelSceneCPU.cuh:107-123
+ *   vrm_set_lighting          <- setupConstantValues                      main/Main.cu:26-42
+ *   vrm_camera_make           <- Camera::Camera                           renderer/camera/Camera.cuh:11-23
+ *   vrm_render[_device|_views]<- runRaymarchingKernel + kernels           main/Main.cu:105-163, renderer/Renderer.cuh:1033-1063
+ *   vrm_trace_rays[_device]   <- rayMarchVoxelScene[LongestAxis]          renderer/Renderer.cuh:338-434, 917-1010
+ *   vrm_lookup                <- StorageStructure::lookupVoxel/doesVoxelSpaceExist  storage/StorageStructure.cuh:12-17
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status (VRM_OK = 0); no exceptions
+ * cross the boundary; the caller owns every buffer it passes; one handle = one device + one stream; a handle is
+ * not thread-safe, distinct handles may be used from distinct threads.  Unless a name ends in _device, pointers
+ * are HOST pointers and the call returns after the result is in the caller's buffer.
+ */
+#ifndef VRM_B200_H
+#define VRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vrm_scene vrm_scene;
+
+enum
+{
+	VRM_OK = 0,
+	VRM_ERR_INVALID = 1, /* bad argument */
+	VRM_ERR_CUDA = 2,    /* CUDA runtime error (no device, launch failure, ...); see vrm_last_error */
+	VRM_ERR_STATE = 3,   /* call not legal in the handle's state (e.g. render before build) */
+	VRM_ERR_NOMEM = 4,   /* device or host allocation failed */
+	VRM_ERR_BUILD = 5    /* structure construction did not converge */
+};
+
+/* StorageType, geometry/VoxelFunctions.cuh:37 */
+enum { VRM_STORAGE_VCS = 0, VRM_STORAGE_HASHTABLE = 1 };
+/* rayMarchFunctionID, main/Main.cu:58-68 */
+enum { VRM_ALGO_LONGEST_AXIS = 0, VRM_ALGO_ORIGINAL = 1 };
+
+/* Value returned by lookups for "no voxel" (EMPTY_KEY / EMPTY_VAL, geometry/VoxelFunctions.cuh:20-21). */
+#define VRM_EMPTY (1u << 30)
+
+/* Camera = the reference's 60-byte struct as 15 floats: origin, lowerLeftCorner, horizontal, vertical, forward
+ * (renderer/camera/Camera.cuh:31-36). */
+#define VRM_CAMERA_FLOATS 15
+
+const char* vrm_error_string(int status);
+/* Text of the last CUDA/runtime error seen by this handle ("" when none). Never NULL. */
+const char* vrm_last_error(const vrm_scene* scene);
+/* 1 when a CUDA device is usable in this process, else 0. */
+int vrm_device_available(void);
+
+int vrm_scene_create(int device, vrm_scene** out);
+int vrm_scene_destroy(vrm_scene* scene);
+
+/* Use a caller-provided cudaStream_t (passed as void*) for all later work of this handle; NULL restores the
+ * handle's own stream.  Lets a host framework time the kernels with its own events. */
+int vrm_scene_set_stream(vrm_scene* scene, void* cuda_stream);
+int vrm_scene_synchronize(vrm_scene* scene);
+
+/* Append voxels in insertion order: xyz = n x 3 int32, rgb = n x uint32 (r<<16|g<<8|b).  Duplicate coordinates:
+ * the last one added wins.  Coordinates must satisfy |c| < 2^23.  Legal only before vrm_scene_build. */
+int vrm_scene_add_voxels(vrm_scene* scene, const int32_t* xyz, const uint32_t* rgb, uint64_t n);
+int vrm_scene_add_voxels_device(vrm_scene* scene, const int32_t* d_xyz, const uint32_t* d_rgb, uint64_t n);
+
+/* Build the chosen structure ON THE GPU (radix sort -> last-wins dedupe -> region directory ->
+ * VCS cluster tables or cuckoo insertion).  build_ms (nullable) receives the device time. */
+int vrm_scene_build(vrm_scene* scene, int storage_type, float* build_ms);
+
+/* diameter^3 = size of the cubic region table, min_coord = lowest region index on any axis (both as in the
+ * reference), filled = non-empty regions, unique_voxels = voxels after last-wins dedupe, bytes = device bytes
+ * held by the built structure.  Any out pointer may be NULL. */
+int vrm_scene_info(const vrm_scene* scene, uint32_t* diameter, int32_t* min_coord, uint32_t* filled,
+                   uint64_t* unique_voxels, uint64_t* bytes);
+
+/* Defaults = main/Main.cu:26-42: direction unit(1,1,1), colour (1,1,1), position (10,10,-10), point light off,
+ * shadows on. */
+int vrm_set_lighting(vrm_scene* scene, const float direction[3], const float colour[3], const float position[3],
+                     int use_point_light, int use_shadows);
+
+/* Host-side helpers evaluated with the reference's operation order in IEEE fp32 (no contraction). */
+int vrm_camera_make(const float origin[3], const float look_at[3], const float up[3], float fov_degrees,
+                    float aspect, float out_camera[VRM_CAMERA_FLOATS]);
+int vrm_make_unit_vector(const float v[3], float out[3]);
+
+/* Render one frame.  rgb_out = H x W x 3 bytes, row 0 = top (renderer/Renderer.cuh:1024-1031).
+ * hits_out (nullable) = H x W x 4 int32: global voxel x,y,z of the first voxel the pixel's primary ray found and
+ * a 0/1 flag.  kernel_ms (nullable) = device time of the render kernel alone. */
+int vrm_render(vrm_scene* scene, const float camera[VRM_CAMERA_FLOATS], const float translation[3], uint32_t scale,
+               int algorithm, uint32_t width, uint32_t height, uint8_t* rgb_out, int32_t* hits_out, float* kernel_ms);
+
+/* Same with DEVICE output buffers; asynchronous on the handle's stream (no synchronisation, no timing). */
+int vrm_render_device(vrm_scene* scene, const float camera[VRM_CAMERA_FLOATS], const float translation[3],
+                      uint32_t scale, int algorithm, uint32_t width, uint32_t height, uint8_t* d_rgb_out,
+                      int32_t* d_hits_out);
+
+/* A batch of views in ONE launch: cameras = n_views x 15 floats (host); d_rgb_out = n_views x H x W x 3 (device);
+ * d_hits_out nullable.  Asynchronous on the handle's stream. */
+int vrm_render_views_device(vrm_scene* scene, const float* cameras, uint32_t n_views, const float translation[3],
+                            uint32_t scale, int algorithm, uint32_t width, uint32_t height, uint8_t* d_rgb_out,
+                            int32_t* d_hits_out);
+
+/* Arbitrary world rays: rays = n x 6 floats (origin xyz, direction xyz).  colour_out = n x uint32, the value the
+ * reference's rayMarchVoxelScene[LongestAxis] returns (0 = background); hits_out nullable as above. */
+int vrm_trace_rays(vrm_scene* scene, const float* rays, uint64_t n, const float translation[3], uint32_t scale,
+                   int algorithm, uint32_t* colour_out, int32_t* hits_out, float* kernel_ms);
+int vrm_trace_rays_device(vrm_scene* scene, const float* d_rays, uint64_t n, const float translation[3],
+                          uint32_t scale, int algorithm, uint32_t* d_colour_out, int32_t* d_hits_out);
+
+/* The storage seam on GLOBAL voxel coordinates: out[i] = colour or VRM_EMPTY; exists_out[i] (nullable) =
+ * doesVoxelSpaceExist (always 1 inside a non-empty region for the hash table; cluster occupancy for the VCS). */
+int vrm_lookup(vrm_scene* scene, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* exists_out);
+
+/* Event counters of the LAST render / trace call made with statistics enabled (vrm_set_statistics(scene, 1)):
+ * out[0] exist checks, [1] exist checks answering false, [2] lookups, [3] lookups that found a voxel,
+ * [4] hash table-2 probes, [5] region-table reads, [6] rays, [7] reserved.  Used for the roofline's algorithmic bytes. */
+int vrm_set_statistics(vrm_scene* scene, int enabled);
+int vrm_get_statistics(vrm_scene* scene, uint64_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRM_B200_H */

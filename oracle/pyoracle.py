@@ -20,8 +20,10 @@ LIBS = {
     "orc": os.path.join(HERE, "liboracle_port.so"),
     "refg": os.path.join(HERE, "_ref", "libvrm_ref_cuda.so"),
     "refgx": os.path.join(HERE, "_ref", "libvrm_ref_cuda_exact.so"),
+    # host compile of the PRODUCT's traversal core (tests/hostsim/hostsim.cpp) -- a device-code debugging aid, not an oracle
+    "sim": os.path.join(HERE, "..", "tests", "hostsim", "libhostsim.so"),
 }
-PREFIX = {"refh": "refh", "orc": "orc", "refg": "refg", "refgx": "refg"}
+PREFIX = {"refh": "refh", "orc": "orc", "refg": "refg", "refgx": "refg", "sim": "sim"}
 
 STORAGE = {"vcs": 0, "hashtable": 1}          # StorageType, VoxelFunctions.cuh:37
 ALGORITHM = {"longestaxis": 0, "original": 1}  # Main.cu:58-68

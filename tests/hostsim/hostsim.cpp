@@ -1,0 +1,302 @@
+// TEST INFRASTRUCTURE ONLY.  Host compile of the product's per-ray traversal core (csrc/vrm_core.cuh, the exact source
+// the sm_100a kernels are built from) so that its arithmetic and control flow can be checked against the oracle in
+// the CPU-only test tier.  Nothing in the product links or calls this; the storage layouts are filled here by a
+// naive sequential builder (the real one is the GPU pipeline in csrc/vrm_build.cu).
+//   g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -fopenmp
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <tuple>
+#include <vector>
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+
+#include "../../voxelraymarcher_b200/csrc/vrm_core.cuh"
+
+using namespace vrm;
+
+namespace {
+
+struct SimScene
+{
+	std::vector<int32_t> xyz;
+	std::vector<uint32_t> rgb;
+	int storage = -1;
+	int32_t minCoord = 0, maxCoord = 0;
+	uint32_t diameter = 0, filled = 0;
+	std::vector<int32_t> regionTable;
+	std::vector<HashRegionDesc> hashDesc;
+	std::vector<unsigned long long> slots;
+	std::vector<uint2> headers;
+	std::vector<uint32_t> clusterMask;
+	std::vector<uint32_t> values;
+	Lighting light;
+	SceneView view() const
+	{
+		SceneView v;
+		v.regionTable = regionTable.data(); v.diameter = diameter; v.minCoord = minCoord;
+		v.hashDesc = hashDesc.data(); v.slots = slots.data();
+		v.headers = headers.data(); v.clusterMask = clusterMask.data(); v.values = values.data();
+		return v;
+	}
+};
+
+Lighting gLight = {{0.57735026f, 0.57735026f, 0.57735026f}, {1, 1, 1}, {10, 10, -10}, 0, 1};
+
+int floordiv64(int v) { return v >= 0 ? v / 64 : -((-v + 63) / 64); }
+
+template <int ST, int ALGO>
+void render_rows(const SimScene& s, const float* cam, const float* tr, float scale, uint32_t W, uint32_t H, uint8_t* rgb, int32_t* hits, uint64_t* counters, uint32_t* lookups, int nThreads)
+{
+	uint64_t total[5] = {0, 0, 0, 0, 0};
+	#pragma omp parallel num_threads(nThreads)
+	{
+		RayCtx<ST, true> c;
+		c.sv = s.view(); c.light = gLight;
+		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
+		uint64_t local[5] = {0, 0, 0, 0, 0};
+		#pragma omp for schedule(dynamic, 1)
+		for (int64_t y = 0; y < (int64_t)H; y++)
+			for (uint32_t x = 0; x < W; x++)
+			{
+				float o[3], d[3];
+				c.reset();
+				primary_ray(cam, x, (uint32_t)y, W, H, o, d);
+				uint32_t color = march_scene<ST, ALGO, true>(c, o, d, scale);
+				size_t p = (size_t)y * W + x;
+				rgb[3 * p] = (uint8_t)(color >> 16); rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF); rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
+				if (hits) memcpy(hits + 4 * p, c.hit, 16);
+				if (lookups) lookups[p] = (uint32_t)c.st.nLookup;
+				local[0] += c.st.nExist; local[1] += c.st.nExistFalse; local[2] += c.st.nLookup; local[3] += c.st.nLookupHit;
+				if (c.st.nLookup > local[4]) local[4] = c.st.nLookup;
+			}
+		#pragma omp critical
+		{
+			for (int i = 0; i < 4; i++) total[i] += local[i];
+			if (local[4] > total[4]) total[4] = local[4];
+		}
+	}
+	if (counters) memcpy(counters, total, sizeof(total));
+}
+
+template <int ST, int ALGO>
+void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, float scale, uint32_t* colour, int32_t* hits, uint64_t* counters, int nThreads)
+{
+	uint64_t total[5] = {0, 0, 0, 0, 0};
+	#pragma omp parallel num_threads(nThreads)
+	{
+		RayCtx<ST, true> c;
+		c.sv = s.view(); c.light = gLight;
+		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
+		uint64_t local[5] = {0, 0, 0, 0, 0};
+		#pragma omp for schedule(dynamic, 256)
+		for (int64_t i = 0; i < (int64_t)n; i++)
+		{
+			c.reset();
+			colour[i] = march_scene<ST, ALGO, true>(c, rays + 6 * i, rays + 6 * i + 3, scale);
+			if (hits) memcpy(hits + 4 * i, c.hit, 16);
+			local[0] += c.st.nExist; local[1] += c.st.nExistFalse; local[2] += c.st.nLookup; local[3] += c.st.nLookupHit;
+			if (c.st.nLookup > local[4]) local[4] = c.st.nLookup;
+		}
+		#pragma omp critical
+		{
+			for (int i = 0; i < 4; i++) total[i] += local[i];
+			if (local[4] > total[4]) total[4] = local[4];
+		}
+	}
+	if (counters) memcpy(counters, total, sizeof(total));
+}
+
+}  // namespace
+
+extern "C" {
+
+void* sim_scene_create() { return new SimScene(); }
+void sim_scene_destroy(void* h) { delete static_cast<SimScene*>(h); }
+
+void sim_scene_add_voxels(void* h, const int32_t* xyz, const uint32_t* rgb, uint64_t n)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	s->xyz.insert(s->xyz.end(), xyz, xyz + 3 * n);
+	s->rgb.insert(s->rgb.end(), rgb, rgb + n);
+}
+
+int sim_scene_build(void* h, int storageType)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage != -1) return 1;
+	size_t n = s->rgb.size();
+	// region -> (cluster-major 18-bit code -> colour), last write wins
+	std::map<std::tuple<int, int, int>, std::map<uint32_t, uint32_t>> regions;
+	for (size_t i = 0; i < n; i++)
+	{
+		int r[3]; uint32_t l[3];
+		for (int a = 0; a < 3; a++)
+		{
+			int v = s->xyz[3 * i + a];
+			r[a] = floordiv64(v);
+			l[a] = (uint32_t)(v - r[a] * 64);
+			s->minCoord = std::min(s->minCoord, r[a]);
+			s->maxCoord = std::max(s->maxCoord, r[a]);
+		}
+		uint32_t cid = ((l[0] >> 3) << 6) | ((l[1] >> 3) << 3) | (l[2] >> 3);
+		uint32_t code = ((l[0] & 7) << 6) | ((l[1] & 7) << 3) | (l[2] & 7);
+		regions[std::make_tuple(r[2], r[1], r[0])][(cid << 9) | code] = s->rgb[i];
+	}
+	s->diameter = (uint32_t)(s->maxCoord - s->minCoord + 1);
+	uint32_t D = s->diameter;
+	s->regionTable.assign((size_t)D * D * D, -1);
+	s->filled = (uint32_t)regions.size();
+	s->headers.assign((size_t)s->filled * 512 * 16, uint2{0, 0});
+	s->clusterMask.assign((size_t)s->filled * 16, 0);
+	int32_t ri = 0;
+	for (auto& kv : regions)
+	{
+		int rz = std::get<0>(kv.first), ry = std::get<1>(kv.first), rx = std::get<2>(kv.first);
+		s->regionTable[(size_t)(rx - s->minCoord) + (size_t)(ry - s->minCoord) * D + (size_t)(rz - s->minCoord) * D * D] = ri;
+		// VCS: colours in (cluster, code) order + per-word {mask, first index}
+		uint2* hdr = s->headers.data() + (size_t)ri * 512 * 16;
+		for (auto& v : kv.second)
+		{
+			uint32_t cid = v.first >> 9, code = v.first & 511;
+			hdr[cid * 16 + (code >> 5)].x |= 1u << (code & 31);
+			s->clusterMask[(size_t)ri * 16 + (cid >> 5)] |= 1u << (cid & 31);
+			s->values.push_back(v.second);
+		}
+		uint32_t running = (uint32_t)(s->values.size() - kv.second.size());
+		for (uint32_t w = 0; w < 512 * 16; w++) { hdr[w].y = running; running += (uint32_t)__builtin_popcount(hdr[w].x); }
+		// cuckoo: sequential insertion with the product's hash functions
+		uint32_t N = (uint32_t)kv.second.size();
+		HashRegionDesc d;
+		d.n = N + N / 4 + 2;
+		d.slotBase = (uint32_t)s->slots.size();
+		s->slots.resize(s->slots.size() + 2 * (size_t)d.n, kEmptySlot);
+		for (uint32_t attempt = 0;; attempt++)
+		{
+			d.seed1 = 0x9E3779B9u * (attempt + 1) + (uint32_t)ri; d.seed2 = 0x7F4A7C15u * (attempt + 1) ^ (uint32_t)ri;
+			std::fill(s->slots.begin() + d.slotBase, s->slots.end(), kEmptySlot);
+			bool ok = true;
+			for (auto& v : kv.second)
+			{
+				uint32_t cid = v.first >> 9, code = v.first & 511;
+				uint32_t x = ((cid >> 6) << 3) | (code >> 6), y = (((cid >> 3) & 7) << 3) | ((code >> 3) & 7), z = ((cid & 7) << 3) | (code & 7);
+				unsigned long long e = ((unsigned long long)((x << 12) | (y << 6) | z) << 32) | v.second;
+				int table = 0, it = 0;
+				for (; it < 500; it++)
+				{
+					uint32_t key = (uint32_t)(e >> 32);
+					size_t idx = table == 0 ? d.slotBase + hash_slot1(key, d.seed1, d.n) : d.slotBase + d.n + hash_slot2(key, d.seed2, d.n);
+					std::swap(e, s->slots[idx]);
+					if (e == kEmptySlot) break;
+					table ^= 1;
+				}
+				if (it == 500) { ok = false; break; }
+			}
+			if (ok) break;
+			if (attempt > 64) return 2;
+		}
+		s->hashDesc.push_back(d);
+		ri++;
+	}
+	s->storage = storageType;
+	return 0;
+}
+
+void sim_scene_info(void* h, uint32_t* diameter, int32_t* minCoord, uint32_t* filled)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	*diameter = s->diameter; *minCoord = s->minCoord; *filled = s->filled;
+}
+
+void sim_set_lighting(const float* dir, const float* color, const float* pos, int usePoint, int useShadows)
+{
+	memcpy(gLight.dir, dir, 12); memcpy(gLight.color, color, 12); memcpy(gLight.pos, pos, 12);
+	gLight.usePoint = usePoint != 0; gLight.useShadows = useShadows != 0;
+}
+
+void sim_make_unit_vector(const float* v, float* out)
+{
+	float l = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+	out[0] = v[0] / l; out[1] = v[1] / l; out[2] = v[2] / l;
+}
+
+void sim_camera_make(const float*, const float*, const float*, float, float, float*) {}  // cameras come from the oracle / product API
+
+int sim_render(void* h, const float* cam, const float* tr, uint32_t scale, int algorithm, uint32_t W, uint32_t H,
+	uint8_t* rgb, int32_t* hits, uint64_t* counters, uint32_t* lookups, int nThreads)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage == -1) return 1;
+	if (nThreads < 1) nThreads = 1;
+	float sc = (float)scale;
+	if (s->storage == kStorageHash)
+	{
+		if (algorithm == kAlgoOriginal) render_rows<kStorageHash, kAlgoOriginal>(*s, cam, tr, sc, W, H, rgb, hits, counters, lookups, nThreads);
+		else render_rows<kStorageHash, kAlgoLongestAxis>(*s, cam, tr, sc, W, H, rgb, hits, counters, lookups, nThreads);
+	}
+	else
+	{
+		if (algorithm == kAlgoOriginal) render_rows<kStorageVcs, kAlgoOriginal>(*s, cam, tr, sc, W, H, rgb, hits, counters, lookups, nThreads);
+		else render_rows<kStorageVcs, kAlgoLongestAxis>(*s, cam, tr, sc, W, H, rgb, hits, counters, lookups, nThreads);
+	}
+	return 0;
+}
+
+int sim_trace_rays(void* h, const float* rays, uint64_t n, const float* tr, uint32_t scale, int algorithm,
+	uint32_t* colour, int32_t* hits, uint64_t* counters, int nThreads)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage == -1) return 1;
+	if (nThreads < 1) nThreads = 1;
+	float sc = (float)scale;
+	if (s->storage == kStorageHash)
+	{
+		if (algorithm == kAlgoOriginal) trace<kStorageHash, kAlgoOriginal>(*s, rays, n, tr, sc, colour, hits, counters, nThreads);
+		else trace<kStorageHash, kAlgoLongestAxis>(*s, rays, n, tr, sc, colour, hits, counters, nThreads);
+	}
+	else
+	{
+		if (algorithm == kAlgoOriginal) trace<kStorageVcs, kAlgoOriginal>(*s, rays, n, tr, sc, colour, hits, counters, nThreads);
+		else trace<kStorageVcs, kAlgoLongestAxis>(*s, rays, n, tr, sc, colour, hits, counters, nThreads);
+	}
+	return 0;
+}
+
+int sim_lookup(void* h, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* exists)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage == -1) return 1;
+	PermIdentity p;
+	for (uint64_t i = 0; i < n; i++)
+	{
+		int reg[3], l[3];
+		for (int a = 0; a < 3; a++) { reg[a] = floordiv64(xyz[3 * i + a]); l[a] = xyz[3 * i + a] - reg[a] * 64; }
+		out[i] = kEmpty;
+		if (exists) exists[i] = 0;
+		if (s->storage == kStorageHash)
+		{
+			RayCtx<kStorageHash, false> c; c.sv = s->view(); c.reset();
+			int32_t ri = region_entry(c, p, reg);
+			if (ri < 0) continue;
+			auto r = load_region<kStorageHash>(c.sv, ri);
+			if (exists) exists[i] = 1;
+			out[i] = lookup_voxel(c, r, p, reg, l[0], l[1], l[2]);
+		}
+		else
+		{
+			RayCtx<kStorageVcs, false> c; c.sv = s->view(); c.reset();
+			int32_t ri = region_entry(c, p, reg);
+			if (ri < 0) continue;
+			auto r = load_region<kStorageVcs>(c.sv, ri);
+			bool e = space_exists(c, r, p, l[0], l[1], l[2]);
+			if (exists) exists[i] = e;
+			if (e) out[i] = lookup_voxel(c, r, p, reg, l[0], l[1], l[2]);
+		}
+	}
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,743 @@
+// vrm_core.cuh -- per-ray traversal core of the B200-native voxel raymarcher.
+//
+// Everything here is __host__ __device__ so that tests/hostsim can compile the very same source for the CPU and
+// single-step it against the oracle; the product only ever runs it inside the sm_100a kernels of vrm_render.cu.
+//
+// Design:
+//  * "Walk space": a ray is stored with its axes permuted so that slot 0/1/2 are the longest/middle/shortest
+//    direction axes (identity permutation for the "original" algorithm).  Every per-component operation of the
+//    reference is axis-symmetric, so the arithmetic is bit-identical, but the longest-axis algorithm's
+//    dynamically indexed gridValues[axis]/axisDiff[axis] (local-memory traffic in the reference build:
+//    1092 LDL / 1844 STL) become plain registers.  Only the storage code and the region-table
+//    index are computed through three per-ray shift/stride registers.
+//  * No virtual dispatch, no function pointers: storage type and algorithm are template parameters.
+//  * IEEE fp32 with NO contraction: every float op goes through vadd/vsub/vmul/vdiv (the *_rn intrinsics on the
+//    device), mirroring the reference's operation order exactly (SURVEY.md §7 hard part 1).
+//
+// Reference file:line citations are relative to /root/reference/VoxelRaymarcher/src.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include <type_traits>
+
+#if defined(__CUDACC__)
+#define VRM_HD __host__ __device__ __forceinline__
+#define VRM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define VRM_HD inline
+#define VRM_HD_NOINLINE
+#endif
+
+namespace vrm
+{
+
+constexpr float kEps = 0.0001f;                // EPSILON, geometry/VoxelFunctions.cuh:19
+constexpr uint32_t kEmpty = 1u << 30;          // EMPTY_KEY / EMPTY_VAL, geometry/VoxelFunctions.cuh:20-21
+constexpr uint32_t kContinue = kEmpty + 2u;    // CONTINUE_VAL, geometry/VoxelFunctions.cuh:23
+constexpr int kRegion = 64;                    // BLOCK_SIZE, geometry/VoxelFunctions.cuh:24
+constexpr int kStorageVcs = 0, kStorageHash = 1;  // StorageType, geometry/VoxelFunctions.cuh:37
+constexpr int kAlgoLongestAxis = 0, kAlgoOriginal = 1;  // main/Main.cu:58-68
+constexpr unsigned long long kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
+
+// ---------------------------------------------------------------- non-contracting fp32
+
+#if defined(__CUDA_ARCH__)
+VRM_HD float vadd(float a, float b) { return __fadd_rn(a, b); }
+VRM_HD float vsub(float a, float b) { return __fsub_rn(a, b); }
+VRM_HD float vmul(float a, float b) { return __fmul_rn(a, b); }
+VRM_HD float vdiv(float a, float b) { return __fdiv_rn(a, b); }
+VRM_HD float vsqrt(float a) { return __fsqrt_rn(a); }
+VRM_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+VRM_HD int popc32(uint32_t a) { return __popc(a); }
+#else
+// Host build (tests/hostsim only): compiled with -ffp-contract=off.
+VRM_HD float vadd(float a, float b) { return a + b; }
+VRM_HD float vsub(float a, float b) { return a - b; }
+VRM_HD float vmul(float a, float b) { return a * b; }
+VRM_HD float vdiv(float a, float b) { return a / b; }
+VRM_HD float vsqrt(float a) { return sqrtf(a); }
+VRM_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+VRM_HD int popc32(uint32_t a) { return __builtin_popcount(a); }
+#endif
+
+VRM_HD float min3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+// o + t * d, the reference's  origin + (t * direction)  (math/Vector3.cuh:105-109,134-138)
+VRM_HD float along(float o, float t, float d) { return vadd(o, vmul(t, d)); }
+
+// ---------------------------------------------------------------- scene description (device pointers)
+
+struct Lighting
+{
+	float dir[3];    // LIGHT_DIRECTION
+	float color[3];  // LIGHT_COLOR
+	float pos[3];    // LIGHT_POSITION
+	int usePoint;    // USE_POINT_LIGHT
+	int useShadows;  // USE_SHADOWS
+};
+
+struct HashRegionDesc  // 16 bytes, one LDG.128 per region entry
+{
+	uint32_t slotBase;  // first 64-bit slot of table 1; table 2 follows at slotBase + n
+	uint32_t n;         // slots per table
+	uint32_t seed1, seed2;
+};
+
+struct SceneView
+{
+	const int32_t* regionTable;  // D^3 entries: dense region index or -1 (index = ux + uy*D + uz*D*D, VoxelSceneCPU.cuh:61-62)
+	uint32_t diameter;
+	int32_t minCoord;
+	// cuckoo hash table ("two-level": region directory -> per-region pair of tables)
+	const HashRegionDesc* hashDesc;
+	const unsigned long long* slots;  // (key18 << 32) | rgb ; kEmptySlot when free
+	// voxel cluster store
+	const uint2* headers;         // [region][512 clusters][16 words] {occupancy mask, index of the word's first colour}
+	const uint32_t* clusterMask;  // [region][16] : bit c set <=> cluster c holds at least one voxel
+	const uint32_t* values;       // colours, sorted by (region, cluster, in-cluster code)
+};
+
+struct Stats
+{
+	unsigned long long nExist, nExistFalse, nLookup, nLookupHit, nProbe2, nRegionReads;
+};
+
+// ---------------------------------------------------------------- axis permutation ("walk space")
+
+// Walk slot i holds world axis axis(i).  cs(i) = shift of that axis inside a 9-bit cluster / in-cluster code
+// (x:6, y:3, z:0 -- VoxelClusterStore.cuh:21-24); the 18-bit hash key uses shift 2*cs(i) (x:12, y:6, z:0).
+struct PermIdentity
+{
+	VRM_HD int axis(int i) const { return i; }
+	VRM_HD int cs(int i) const { return 6 - 3 * i; }
+	VRM_HD uint32_t stride(int i, uint32_t D) const { return i == 0 ? 1u : (i == 1 ? D : D * D); }
+};
+
+struct PermRuntime
+{
+	int a0, a1, a2;
+	VRM_HD int axis(int i) const { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
+	VRM_HD int cs(int i) const { return 6 - 3 * axis(i); }
+	VRM_HD uint32_t stride(int i, uint32_t D) const
+	{
+		int a = axis(i);
+		return a == 0 ? 1u : (a == 1 ? D : D * D);
+	}
+};
+
+// Ray::convertRayToLongestAxisDirection, renderer/rays/Ray.cuh:19-71 (strict '>' tie rules): slot 0 = longest,
+// slot 1 = "shortAxis1" (middle), slot 2 = "shortAxis2" (shortest).
+VRM_HD PermRuntime rank_axes(float dx, float dy, float dz)
+{
+	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	PermRuntime p;
+	if (ax > ay && ax > az) { p.a0 = 0; if (ay > az) { p.a1 = 1; p.a2 = 2; } else { p.a1 = 2; p.a2 = 1; } }
+	else if (ay > az)       { p.a0 = 1; if (ax > az) { p.a1 = 0; p.a2 = 2; } else { p.a1 = 2; p.a2 = 0; } }
+	else                    { p.a0 = 2; if (ax > ay) { p.a1 = 0; p.a2 = 1; } else { p.a1 = 1; p.a2 = 0; } }
+	return p;
+}
+
+template <class T> VRM_HD T pick3(int a, T v0, T v1, T v2) { return a == 0 ? v0 : (a == 1 ? v1 : v2); }
+
+// world (x,y,z) -> walk slots
+template <class P, class T> VRM_HD void to_walk(const P& p, const T* xyz, T* w)
+{
+	w[0] = pick3(p.axis(0), xyz[0], xyz[1], xyz[2]);
+	w[1] = pick3(p.axis(1), xyz[0], xyz[1], xyz[2]);
+	w[2] = pick3(p.axis(2), xyz[0], xyz[1], xyz[2]);
+}
+// walk slots -> world (x,y,z)
+template <class P, class T> VRM_HD void to_world(const P& p, const T* w, T* xyz)
+{
+	int a0 = p.axis(0), a1 = p.axis(1);
+	xyz[0] = a0 == 0 ? w[0] : (a1 == 0 ? w[1] : w[2]);
+	xyz[1] = a0 == 1 ? w[0] : (a1 == 1 ? w[1] : w[2]);
+	xyz[2] = a0 == 2 ? w[0] : (a1 == 2 ? w[1] : w[2]);
+}
+
+// ---------------------------------------------------------------- storage access
+
+VRM_HD uint32_t mix_a(uint32_t h)
+{
+	h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+	return h;
+}
+VRM_HD uint32_t mix_b(uint32_t h)
+{
+	h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+	return h;
+}
+// Slot index inside one table: multiply-shift range reduction instead of the reference's four integer modulos
+// per probe (CuckooHashTable.cuh:62,69).
+VRM_HD uint32_t hash_slot1(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32(mix_a(key ^ seed), n); }
+VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32(mix_b(key ^ seed), n); }
+
+template <int ST> struct RegionRef;
+
+template <> struct RegionRef<kStorageHash>
+{
+	const unsigned long long* t1;
+	const unsigned long long* t2;
+	uint32_t n, seed1, seed2;
+};
+
+template <> struct RegionRef<kStorageVcs>
+{
+	const uint2* hdr;
+	const uint32_t* cmask;
+};
+
+template <int ST> VRM_HD RegionRef<ST> load_region(const SceneView& sv, int32_t ri);
+
+template <> VRM_HD RegionRef<kStorageHash> load_region<kStorageHash>(const SceneView& sv, int32_t ri)
+{
+#if defined(__CUDA_ARCH__)
+	uint4 raw = __ldg(reinterpret_cast<const uint4*>(sv.hashDesc) + ri);
+	HashRegionDesc d = {raw.x, raw.y, raw.z, raw.w};
+#else
+	HashRegionDesc d = sv.hashDesc[ri];
+#endif
+	RegionRef<kStorageHash> r;
+	r.t1 = sv.slots + d.slotBase;
+	r.t2 = r.t1 + d.n;
+	r.n = d.n; r.seed1 = d.seed1; r.seed2 = d.seed2;
+	return r;
+}
+
+template <> VRM_HD RegionRef<kStorageVcs> load_region<kStorageVcs>(const SceneView& sv, int32_t ri)
+{
+	RegionRef<kStorageVcs> r;
+	r.hdr = sv.headers + (size_t)ri * (512 * 16);
+	r.cmask = sv.clusterMask + (size_t)ri * 16;
+	return r;
+}
+
+template <class T> VRM_HD T ldg(const T* p)
+{
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
+
+// ---------------------------------------------------------------- per-ray context
+
+template <int ST, bool STATS> struct RayCtx
+{
+	SceneView sv;
+	Lighting light;
+	float translation[3];
+	int32_t hit[4];  // first voxel found by this ray (global x,y,z, flag) -- SURVEY.md F6
+	Stats st;
+
+	VRM_HD void reset()
+	{
+		hit[0] = hit[1] = hit[2] = hit[3] = 0;
+		if (STATS) { st.nExist = st.nExistFalse = st.nLookup = st.nLookupHit = st.nProbe2 = st.nRegionReads = 0; }
+	}
+};
+
+// StorageStructure::doesVoxelSpaceExist (storage/StorageStructure.cuh:36-39,49-52; VoxelClusterStore.cuh:93-99)
+template <int ST, bool STATS, class P>
+VRM_HD bool space_exists(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, int g0, int g1, int g2)
+{
+	bool e = true;
+	if constexpr (ST == kStorageVcs)
+	{
+		const RegionRef<kStorageVcs>& rv = r;
+		uint32_t cid = ((uint32_t)(g0 >> 3) << p.cs(0)) | ((uint32_t)(g1 >> 3) << p.cs(1)) | ((uint32_t)(g2 >> 3) << p.cs(2));
+		e = (ldg(rv.cmask + (cid >> 5)) >> (cid & 31)) & 1u;
+	}
+	if (STATS) { c.st.nExist++; if (!e) c.st.nExistFalse++; }
+	return e;
+}
+
+// StorageStructure::lookupVoxel (CuckooHashTable.cuh:59-76; VoxelClusterStore.cuh:101-135): colour or kEmpty.
+// g0..g2 are region-local coordinates in walk order; reg[] the region in walk order (for the hit record).
+template <int ST, bool STATS, class P>
+VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, const int* reg, int g0, int g1, int g2)
+{
+	uint32_t v = kEmpty;
+	if constexpr (ST == kStorageHash)
+	{
+		const RegionRef<kStorageHash>& rh = r;
+		uint32_t key = ((uint32_t)g0 << (2 * p.cs(0))) | ((uint32_t)g1 << (2 * p.cs(1))) | ((uint32_t)g2 << (2 * p.cs(2)));
+		// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
+		unsigned long long e1 = ldg(rh.t1 + hash_slot1(key, rh.seed1, rh.n));
+		unsigned long long e2 = ldg(rh.t2 + hash_slot2(key, rh.seed2, rh.n));
+		if ((uint32_t)(e1 >> 32) == key) v = (uint32_t)e1;
+		else if ((uint32_t)(e2 >> 32) == key) v = (uint32_t)e2;
+		if (STATS) c.st.nProbe2++;
+	}
+	else
+	{
+		const RegionRef<kStorageVcs>& rv = r;
+		uint32_t cid = ((uint32_t)(g0 >> 3) << p.cs(0)) | ((uint32_t)(g1 >> 3) << p.cs(1)) | ((uint32_t)(g2 >> 3) << p.cs(2));
+		uint32_t code = ((uint32_t)(g0 & 7) << p.cs(0)) | ((uint32_t)(g1 & 7) << p.cs(1)) | ((uint32_t)(g2 & 7) << p.cs(2));
+		uint2 h = ldg(rv.hdr + cid * 16 + (code >> 5));
+		uint32_t bit = code & 31;
+		if ((h.x >> bit) & 1u) v = ldg(c.sv.values + h.y + popc32(h.x & ((1u << bit) - 1u)));
+	}
+	if (STATS) c.st.nLookup++;
+	if (v != kEmpty)
+	{
+		if (STATS) c.st.nLookupHit++;
+		if (!c.hit[3])
+		{
+			int gw[3] = {reg[0] * kRegion + g0, reg[1] * kRegion + g1, reg[2] * kRegion + g2};
+			int gx[3];
+			to_world(p, gw, gx);
+			c.hit[0] = gx[0]; c.hit[1] = gx[1]; c.hit[2] = gx[2]; c.hit[3] = 1;
+		}
+	}
+	return v;
+}
+
+// VoxelScene::isRayInScene + getRegionStorageStructure (renderer/Renderer.cuh:29-44): -2 = outside the table,
+// -1 = empty region, else dense region index.
+template <int ST, bool STATS, class P>
+VRM_HD int32_t region_entry(RayCtx<ST, STATS>& c, const P& p, const int* reg)
+{
+	uint32_t D = c.sv.diameter;
+	uint32_t u0 = (uint32_t)(reg[0] - c.sv.minCoord), u1 = (uint32_t)(reg[1] - c.sv.minCoord), u2 = (uint32_t)(reg[2] - c.sv.minCoord);
+	if (!(u0 < D && u1 < D && u2 < D)) return -2;
+	if (STATS) c.st.nRegionReads++;
+	return ldg(c.sv.regionTable + (u0 * p.stride(0, D) + u1 * p.stride(1, D) + u2 * p.stride(2, D)));
+}
+
+// ---------------------------------------------------------------- lighting (renderer/Renderer.cuh:57-86,237-258)
+
+VRM_HD uint32_t vec_to_rgb(float r, float g, float b)  // VoxelFunctions.cuh:76-82
+{
+	uint32_t ir = (uint32_t)vmul(r, 255.0f), ig = (uint32_t)vmul(g, 255.0f), ib = (uint32_t)vmul(b, 255.0f);
+	return (ir << 16) | (ig << 8) | ib;
+}
+
+// normalAxis / normalSign are in WORLD axes; hitLocal = hit position in region-local WORLD axes; regW = region (world axes)
+VRM_HD uint32_t apply_lighting(const Lighting& L, const float* translation, uint32_t voxelColor, int normalAxis, float normalSign,
+                               const float* hitLocal, const int* regW)
+{
+	float cr = vdiv((float)(voxelColor >> 16), 255.0f);           // VoxelFunctions.cuh:54-74
+	float cg = vdiv((float)((voxelColor >> 8) & 0xFF), 255.0f);
+	float cb = vdiv((float)(voxelColor & 0xFF), 255.0f);
+	float n[3] = {0.0f, 0.0f, 0.0f};
+	n[0] = normalAxis == 0 ? normalSign : 0.0f;
+	n[1] = normalAxis == 1 ? normalSign : 0.0f;
+	n[2] = normalAxis == 2 ? normalSign : 0.0f;
+	if (L.usePoint)  // Renderer.cuh:68-86
+	{
+		float t[3];
+		for (int i = 0; i < 3; i++)
+		{
+			float regionWorld = vadd(translation[i], (float)(regW[i] * kRegion));  // Renderer.cuh:413
+			float hit = vadd(regionWorld, hitLocal[i]);                              // Renderer.cuh:88-91
+			t[i] = vsub(L.pos[i], hit);
+		}
+		float distance = vsqrt(vadd(vadd(vmul(t[0], t[0]), vmul(t[1], t[1])), vmul(t[2], t[2])));
+		float ld[3] = {vdiv(t[0], distance), vdiv(t[1], distance), vdiv(t[2], distance)};
+		float attenuation = vdiv(1.0f, vadd(vadd(1.0f, vmul(0.045f, distance)), vmul(0.0075f, vmul(distance, distance))));
+		float diff = fmaxf(vadd(vadd(vmul(n[0], ld[0]), vmul(n[1], ld[1])), vmul(n[2], ld[2])), 0.0f);
+		float r = vmul(vmul(attenuation, vmul(diff, L.color[0])), cr);
+		float g = vmul(vmul(attenuation, vmul(diff, L.color[1])), cg);
+		float b = vmul(vmul(attenuation, vmul(diff, L.color[2])), cb);
+		return vec_to_rgb(r, g, b);
+	}
+	// Renderer.cuh:57-66
+	float diff = fmaxf(vadd(vadd(vmul(n[0], L.dir[0]), vmul(n[1], L.dir[1])), vmul(n[2], L.dir[2])), 0.0f);
+	return vec_to_rgb(vmul(cr, vmul(diff, L.color[0])), vmul(cg, vmul(diff, L.color[1])), vmul(cb, vmul(diff, L.color[2])));
+}
+
+// getNormalFromTValues (Renderer.cuh:237-247) evaluated in walk space: the reference tests X, then Y, else Z,
+// so pick the lowest WORLD axis whose t equals tMin, falling back to Z.
+template <class P> VRM_HD int normal_axis_from_t(const P& p, float t0, float t1, float t2, float tMin)
+{
+	int m = 0;
+	if (t0 == tMin) m |= 1 << p.axis(0);
+	if (t1 == tMin) m |= 1 << p.axis(1);
+	if (t2 == tMin) m |= 1 << p.axis(2);
+	return (m & 1) ? 0 : ((m & 2) ? 1 : 2);
+}
+
+// ---------------------------------------------------------------- shared walk helpers
+
+VRM_HD bool ray_in_region(const float* o)  // Renderer.cuh:93-98
+{
+	return o[0] >= 0.0f && o[0] < (float)kRegion && o[1] >= 0.0f && o[1] < (float)kRegion && o[2] >= 0.0f && o[2] < (float)kRegion;
+}
+VRM_HD bool grid_in_region(int x, int y, int z)  // Renderer.cuh:436-439
+{
+	return (uint32_t)x < (uint32_t)kRegion && (uint32_t)y < (uint32_t)kRegion && (uint32_t)z < (uint32_t)kRegion;
+}
+VRM_HD float next_edge(float d, float v)  // Renderer.cuh:47-55,263-265
+{
+	return d > 0.0f ? vadd(ceilf(v), kEps) : vsub(floorf(v), kEps);
+}
+template <bool GUARD> VRM_HD float t_to(float next, float o, float d)  // Renderer.cuh:113-115 (guarded) / 273-275
+{
+	float t = vdiv(vsub(next, o), d);
+	if (GUARD) t = (d != 0.0f) ? t : INFINITY;
+	return t;
+}
+VRM_HD int cluster_edge(float d, int v)  // Renderer.cuh:293-295
+{
+	return d > 0.0f ? ((v / 8) + 1) * 8 : (v / 8) * 8;
+}
+
+// Renderer.cuh:421-429: move region coordinates by floor(o / 64) and rebase the local position
+VRM_HD void rebase_region(float* o, int* reg)
+{
+	for (int i = 0; i < 3; i++)
+	{
+		int diff = (int)floorf(vdiv(o[i], (float)kRegion));
+		reg[i] += diff;
+		o[i] = vmul(1.0f, vsub(o[i], (float)(diff * kRegion)));  // convertRayToLocalSpace(.., scale 1), Ray.cuh:14-17
+	}
+}
+
+// Null-region skip, Renderer.cuh:384-410 (GUARD: 185-211).  On return ri >= 0 (a stored region) or -2 (left the scene).
+template <int ST, bool STATS, class P, bool GUARD>
+VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, const float* d, int* reg, int32_t ri)
+{
+	while (ri == -1)
+	{
+		float n0 = d[0] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
+		float n1 = d[1] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
+		float n2 = d[2] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
+		float tMin = min3(t_to<GUARD>(n0, o[0], d[0]), t_to<GUARD>(n1, o[1], d[1]), t_to<GUARD>(n2, o[2], d[2]));
+		o[0] = along(o[0], tMin, d[0]); o[1] = along(o[1], tMin, d[1]); o[2] = along(o[2], tMin, d[2]);
+		rebase_region(o, reg);
+		ri = region_entry(c, p, reg);
+	}
+	return ri;
+}
+
+// ---------------------------------------------------------------- "original" traversal
+
+// The step loop shared by rayMarchVoxelGrid (Renderer.cuh:260-336, GUARD=false) and shadowRayMarchVoxelGrid
+// (Renderer.cuh:100-172, GUARD=true).  Returns the raw voxel colour or kEmpty; t[0..3] = the OUTER tX,tY,tZ,tMin
+// of the hit step (stale after a cluster skip, exactly as in the reference, SURVEY.md §7 hard part 3).
+template <int ST, bool STATS, class P, bool GUARD>
+VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const float* d, const int* reg, float* t)
+{
+	float t0 = t_to<GUARD>(next_edge(d[0], o[0]), o[0], d[0]);
+	float t1 = t_to<GUARD>(next_edge(d[1], o[1]), o[1], d[1]);
+	float t2 = t_to<GUARD>(next_edge(d[2], o[2]), o[2], d[2]);
+	float tMin = min3(t0, t1, t2);
+	float s = vadd(tMin, kEps);
+	o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
+	while (ray_in_region(o))
+	{
+		int v0 = (int)o[0], v1 = (int)o[1], v2 = (int)o[2];
+		if (!space_exists(c, r, p, v0, v1, v2))
+		{
+			float u0 = t_to<GUARD>((float)cluster_edge(d[0], v0), o[0], d[0]);
+			float u1 = t_to<GUARD>((float)cluster_edge(d[1], v1), o[1], d[1]);
+			float u2 = t_to<GUARD>((float)cluster_edge(d[2], v2), o[2], d[2]);
+			float su = vadd(min3(u0, u1, u2), kEps);
+			o[0] = along(o[0], su, d[0]); o[1] = along(o[1], su, d[1]); o[2] = along(o[2], su, d[2]);
+			continue;
+		}
+		uint32_t col = lookup_voxel(c, r, p, reg, v0, v1, v2);
+		if (col != kEmpty)
+		{
+			t[0] = t0; t[1] = t1; t[2] = t2; t[3] = tMin;
+			return col;
+		}
+		t0 = t_to<GUARD>(next_edge(d[0], o[0]), o[0], d[0]);
+		t1 = t_to<GUARD>(next_edge(d[1], o[1]), o[1], d[1]);
+		t2 = t_to<GUARD>(next_edge(d[2], o[2]), o[2], d[2]);
+		tMin = min3(t0, t1, t2);
+		s = vadd(tMin, kEps);
+		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
+	}
+	return kEmpty;
+}
+
+// What a primary march reports on a hit; lighting and the shadow ray are applied ONCE, in march_scene, instead of
+// at each of the reference's eight hit sites (keeps the kernel small and the warp converged).
+struct HitInfo
+{
+	float pos[3];   // hit position, region-local, walk space (the "rayOrigin" handed to applyLighting / the shadow ray)
+	int nAxisW;     // normal axis in WORLD axes
+	float nSign;    // +-1
+	int laShadow;   // 1: isInShadowRayMarchVoxelSceneLongestAxis, 0: isInShadowOriginalRayMarch
+};
+
+// rayMarchVoxelGrid, Renderer.cuh:260-336 (the hit's lighting + shadow are applied by the caller)
+template <int ST, bool STATS, class P>
+VRM_HD uint32_t march_original(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const float* d, const int* reg, HitInfo& h)
+{
+	float t[4];
+	uint32_t col = march_steps<ST, STATS, P, false>(c, r, p, o, d, reg, t);
+	if (col == kEmpty) return kEmpty;
+	h.nAxisW = normal_axis_from_t(p, t[0], t[1], t[2], t[3]);  // Renderer.cuh:312
+	float dn = p.axis(0) == h.nAxisW ? d[0] : (p.axis(1) == h.nAxisW ? d[1] : d[2]);
+	h.nSign = copysignf(1.0f, -dn);
+	h.pos[0] = o[0]; h.pos[1] = o[1]; h.pos[2] = o[2];        // Renderer.cuh:314-315
+	h.laShadow = 0;
+	return col;
+}
+
+// ---------------------------------------------------------------- "longest axis" traversal (walk slot 0 = L, 1 = M, 2 = S)
+
+struct LaState
+{
+	float oo[3], od[3];  // oldRay origin / longest-axis-scaled direction
+	float ro[3];         // ray origin (its direction equals od)
+	int g[3], ad[3];     // gridValues, axisDiff
+};
+
+// performVoxelSpaceJump (Renderer.cuh:696-751) / performShadowVoxelSpaceJump (Renderer.cuh:441-492)
+template <int ST, bool STATS, bool SHADOW>
+VRM_HD uint32_t voxel_space_jump(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, LaState& s, float* origO, const int* reg, HitInfo& h)
+{
+	float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, tMin = 0.0f;
+	while (!space_exists(c, r, p, s.g[0], s.g[1], s.g[2]))
+	{
+		t0 = vdiv(vsub((float)cluster_edge(s.od[0], s.g[0]), s.oo[0]), s.od[0]);
+		t1 = vdiv(vsub((float)cluster_edge(s.od[1], s.g[1]), s.oo[1]), s.od[1]);
+		t2 = vdiv(vsub((float)cluster_edge(s.od[2], s.g[2]), s.oo[2]), s.od[2]);
+		tMin = vadd(min3(t0, t1, t2), kEps);
+		s.oo[0] = along(s.oo[0], tMin, s.od[0]); s.oo[1] = along(s.oo[1], tMin, s.od[1]); s.oo[2] = along(s.oo[2], tMin, s.od[2]);
+		s.g[0] = (int)floorf(s.oo[0]); s.g[1] = (int)floorf(s.oo[1]); s.g[2] = (int)floorf(s.oo[2]);
+		if (!grid_in_region(s.g[0], s.g[1], s.g[2]))
+		{
+			origO[0] = s.oo[0]; origO[1] = s.oo[1]; origO[2] = s.oo[2];
+			return kEmpty;
+		}
+	}
+	uint32_t col = lookup_voxel(c, r, p, reg, s.g[0], s.g[1], s.g[2]);
+	if (col != kEmpty)
+	{
+		if (!SHADOW)
+		{
+			// tMin already carries +EPSILON (Renderer.cuh:716,736), so this normally falls through to the Z normal
+			h.nAxisW = normal_axis_from_t(p, t0, t1, t2, tMin);
+			float dn = p.axis(0) == h.nAxisW ? s.od[0] : (p.axis(1) == h.nAxisW ? s.od[1] : s.od[2]);
+			h.nSign = copysignf(1.0f, -dn);
+			h.pos[0] = s.oo[0]; h.pos[1] = s.oo[1]; h.pos[2] = s.oo[2];  // Renderer.cuh:737-738
+			h.laShadow = 1;
+		}
+		return col;
+	}
+	// re-snap to the longest axis, Renderer.cuh:742-747
+	float tNext = s.od[0] > 0.0f ? vdiv(vsub(ceilf(s.oo[0]), s.oo[0]), s.od[0]) : vdiv(vsub(floorf(s.oo[0]), s.oo[0]), s.od[0]);
+	float tt = vadd(tNext, kEps);
+	s.ro[0] = along(s.oo[0], tt, s.od[0]); s.ro[1] = along(s.oo[1], tt, s.od[1]); s.ro[2] = along(s.oo[2], tt, s.od[2]);
+	s.ad[1] = (int)s.ro[1] - s.g[1];
+	s.ad[2] = (int)s.ro[2] - s.g[2];
+	return kContinue;
+}
+
+// rayMarchVoxelGridLongestAxis (Renderer.cuh:760-915) / shadowRayMarchVoxelGridLongestAxis (Renderer.cuh:495-631).
+// o/d/reg are in walk space of p (slot 0 = longest axis of d).
+//
+// The reference spells the per-iteration voxel tests out as four sub-cases with seven copies of the same
+// "bump one axis, test the voxel space, look the voxel up" unit.  Here the sub-case only selects the ORDER of
+// slots to test (packed 2 bits each into `seq`); one shared test site then runs 1-3 times.  Same tests in the same
+// order, but lanes of a warp that are in different sub-cases execute the same instructions instead of serialising.
+template <int ST, bool STATS, bool SHADOW>
+VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, float* o, const float* d, const int* reg, HitInfo& h)
+{
+	LaState s;
+	float k = vdiv(1.0f, fabsf(d[0]));  // Ray.cuh:37,52,67
+	s.od[0] = vmul(k, d[0]); s.od[1] = vmul(k, d[1]); s.od[2] = vmul(k, d[2]);
+	s.oo[0] = o[0]; s.oo[1] = o[1]; s.oo[2] = o[2];
+	s.g[0] = (int)o[0]; s.g[1] = (int)o[1]; s.g[2] = (int)o[2];
+	s.ad[0] = d[0] < 0.0f ? -1 : 1;
+	// snap the longest axis to the grid, Renderer.cuh:776-779
+	float t = s.ad[0] > 0 ? vdiv(vsub(vadd(vadd((float)s.g[0], kEps), 1.0f), o[0]), 1.0f)
+	                      : vdiv(vsub(vsub((float)s.g[0], kEps), o[0]), -1.0f);
+	s.ro[0] = along(s.oo[0], t, s.od[0]); s.ro[1] = along(s.oo[1], t, s.od[1]); s.ro[2] = along(s.oo[2], t, s.od[2]);
+	s.ad[1] = (int)s.ro[1] - s.g[1];
+	s.ad[2] = (int)s.ro[2] - s.g[2];
+	const bool roundDown = s.od[1] < 0.0f;  // Renderer.cuh:784
+
+	while (grid_in_region(s.g[0] + s.ad[0], s.g[1] + s.ad[1], s.g[2] + s.ad[2]))
+	{
+		// slots to test this iteration, first test in the low bits; the longest axis (slot 0) is always last
+		uint32_t seq;
+		int nTests;
+		if (s.ad[2] != 0 && s.ad[1] != 0)  // Renderer.cuh:792-805
+		{
+			float rounded = roundDown ? floorf(s.oo[1]) : ceilf(s.oo[1]);
+			float t1 = vdiv(vsub(rounded, s.oo[1]), s.od[1]);
+			float shortestPosition = vadd(s.oo[2], vmul(s.od[2], t1));
+			int shorterDiff = (int)floorf(shortestPosition) - s.g[2];
+			seq = shorterDiff != 0 ? (2u | (1u << 2)) : (1u | (2u << 2));
+			nTests = 3;
+		}
+		else if (s.ad[1] != 0) { seq = 1u; nTests = 2; }  // Renderer.cuh:844
+		else if (s.ad[2] != 0) { seq = 2u; nTests = 2; }  // Renderer.cuh:865
+		else { seq = 0u; nTests = 1; }
+		bool again = false;
+		for (int i = 0; i < nTests; i++)
+		{
+			int slot = (int)(seq & 3u);
+			seq >>= 2;
+			s.g[0] += slot == 0 ? s.ad[0] : 0;
+			s.g[1] += slot == 1 ? s.ad[1] : 0;
+			s.g[2] += slot == 2 ? s.ad[2] : 0;
+			if (!space_exists(c, r, p, s.g[0], s.g[1], s.g[2]))
+			{
+				uint32_t j = voxel_space_jump<ST, STATS, SHADOW>(c, r, p, s, o, reg, h);
+				if (j != kContinue) return j;
+				again = true;  // `continue` of the reference's while loop
+				break;
+			}
+			uint32_t col = lookup_voxel(c, r, p, reg, s.g[0], s.g[1], s.g[2]);
+			if (col != kEmpty)
+			{
+				if (!SHADOW)
+				{
+					float odS = pick3(slot, s.od[0], s.od[1], s.od[2]);
+					h.nAxisW = p.axis(slot);
+					h.nSign = copysignf(1.0f, -odS);
+					if (slot == 0) { h.pos[0] = s.ro[0]; h.pos[1] = s.ro[1]; h.pos[2] = s.ro[2]; }  // Renderer.cuh:899
+					else
+					{
+						// getLocalHitLocation, Renderer.cuh:753-758
+						float ooS = pick3(slot, s.oo[0], s.oo[1], s.oo[2]);
+						float tl = odS > 0.0f ? vdiv(vsub(ceilf(ooS), ooS), odS) : vdiv(vsub(floorf(ooS), ooS), odS);
+						h.pos[0] = along(s.oo[0], tl, s.od[0]); h.pos[1] = along(s.oo[1], tl, s.od[1]); h.pos[2] = along(s.oo[2], tl, s.od[2]);
+					}
+					h.laShadow = 1;
+				}
+				return col;
+			}
+		}
+		if (again) continue;
+		// Renderer.cuh:903-908
+		s.oo[0] = s.ro[0]; s.oo[1] = s.ro[1]; s.oo[2] = s.ro[2];
+		s.ro[0] = vadd(s.ro[0], s.od[0]); s.ro[1] = vadd(s.ro[1], s.od[1]); s.ro[2] = vadd(s.ro[2], s.od[2]);
+		s.ad[1] = (int)s.ro[1] - s.g[1];
+		s.ad[2] = (int)s.ro[2] - s.g[2];
+	}
+	// Renderer.cuh:911-914 / 627-630: finish the region with the original algorithm from oldRay's origin
+	o[0] = s.oo[0]; o[1] = s.oo[1]; o[2] = s.oo[2];
+	if (SHADOW)
+	{
+		float tt[4];
+		return march_steps<ST, STATS, PermRuntime, true>(c, r, p, o, d, reg, tt);
+	}
+	return march_original<ST, STATS, PermRuntime>(c, r, p, o, d, reg, h);
+}
+
+// isInShadowOriginalRayMarch (Renderer.cuh:174-235; LA = false, zero-direction guards) and
+// isInShadowRayMarchVoxelSceneLongestAxis (Renderer.cuh:633-694; LA = true, no guards in the region walk).
+// originW / regW are in WORLD axes; the walk itself runs in the permutation of the light direction.
+template <int ST, bool STATS, bool LA>
+VRM_HD bool in_shadow(RayCtx<ST, STATS>& c, const float* originW, const int* regW)
+{
+	if (!c.light.useShadows) return false;
+	using P = typename std::conditional<LA, PermRuntime, PermIdentity>::type;
+	P p;
+	if constexpr (LA) p = rank_axes(c.light.dir[0], c.light.dir[1], c.light.dir[2]);
+	float o[3], d[3];
+	int reg[3];
+	to_walk(p, originW, o); to_walk(p, c.light.dir, d); to_walk(p, regW, reg);
+	int32_t ri = region_entry(c, p, reg);
+	while (ri != -2)
+	{
+		ri = skip_null_regions<ST, STATS, P, !LA>(c, p, o, d, reg, ri);
+		if (ri == -2) return false;
+		RegionRef<ST> r = load_region<ST>(c.sv, ri);
+		uint32_t col;
+		if constexpr (LA)
+		{
+			HitInfo unused;
+			col = march_longest_axis<ST, STATS, true>(c, r, p, o, d, reg, unused);
+		}
+		else
+		{
+			float t[4];
+			col = march_steps<ST, STATS, P, true>(c, r, p, o, d, reg, t);
+		}
+		if (col != kEmpty) return true;
+		rebase_region(o, reg);
+		ri = region_entry(c, p, reg);
+	}
+	return false;
+}
+
+// ---------------------------------------------------------------- scene walk
+
+// rayMarchVoxelScene (Renderer.cuh:338-434) / rayMarchVoxelSceneLongestAxis (Renderer.cuh:917-1010).
+// originW/dirW: WORLD ray (before the scene transform).  Returns the pixel colour (0 = background).
+template <int ST, int ALGO, bool STATS>
+VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
+{
+	using P = typename std::conditional<ALGO == kAlgoOriginal, PermIdentity, PermRuntime>::type;
+	P p;
+	if constexpr (ALGO != kAlgoOriginal) p = rank_axes(dirW[0], dirW[1], dirW[2]);
+	// Ray::convertRayToLocalSpace, Ray.cuh:14-17
+	float sW[3] = {vmul(scale, vsub(originW[0], c.translation[0])), vmul(scale, vsub(originW[1], c.translation[1])), vmul(scale, vsub(originW[2], c.translation[2]))};
+	float o[3], d[3];
+	to_walk(p, sW, o); to_walk(p, dirW, d);
+	int reg[3] = {(int)floorf(vdiv(o[0], (float)kRegion)), (int)floorf(vdiv(o[1], (float)kRegion)), (int)floorf(vdiv(o[2], (float)kRegion))};
+	const int minC = c.sv.minCoord;
+	const uint32_t D = c.sv.diameter;
+	// scene-entry loop, Renderer.cuh:349-373
+	while (reg[0] - minC < 0 || reg[1] - minC < 0 || reg[2] - minC < 0 ||
+	       (uint32_t)(reg[0] - minC) > D - 1 || (uint32_t)(reg[1] - minC) > D - 1 || (uint32_t)(reg[2] - minC) > D - 1)
+	{
+		int far = (int)(D + (uint32_t)minC);
+		float t0 = vdiv(vsub((float)((d[0] < 0.0f ? far : minC) * kRegion), o[0]), d[0]);
+		float t1 = vdiv(vsub((float)((d[1] < 0.0f ? far : minC) * kRegion), o[1]), d[1]);
+		float t2 = vdiv(vsub((float)((d[2] < 0.0f ? far : minC) * kRegion), o[2]), d[2]);
+		if (t0 <= 0.0f) t0 = INFINITY;
+		if (t1 <= 0.0f) t1 = INFINITY;
+		if (t2 <= 0.0f) t2 = INFINITY;
+		float tMin = min3(t0, t1, t2);
+		if (tMin == INFINITY) return 0;
+		float s = vadd(tMin, kEps);
+		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
+		reg[0] = (int)floorf(vdiv(o[0], (float)kRegion)); reg[1] = (int)floorf(vdiv(o[1], (float)kRegion)); reg[2] = (int)floorf(vdiv(o[2], (float)kRegion));
+	}
+	// to region-local coordinates, Renderer.cuh:376-378
+	for (int i = 0; i < 3; i++) o[i] = vmul(1.0f, vsub(o[i], (float)(reg[i] * kRegion)));
+	int32_t ri = region_entry(c, p, reg);
+	while (ri != -2)
+	{
+		ri = skip_null_regions<ST, STATS, P, false>(c, p, o, d, reg, ri);
+		if (ri == -2) return 0;
+		RegionRef<ST> r = load_region<ST>(c.sv, ri);
+		HitInfo h;
+		uint32_t col;
+		if constexpr (ALGO == kAlgoOriginal) col = march_original<ST, STATS, P>(c, r, p, o, d, reg, h);
+		else col = march_longest_axis<ST, STATS, false>(c, r, p, o, d, reg, h);
+		if (col != kEmpty)
+		{
+			// applyLighting(...) * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion)  (Renderer.cuh:314-315,821-822,...)
+			float hitW[3];
+			int regW[3];
+			to_world(p, h.pos, hitW); to_world(p, reg, regW);
+			uint32_t lit = apply_lighting(c.light, c.translation, col, h.nAxisW, h.nSign, hitW, regW);
+			bool shadowed;
+			if constexpr (ALGO == kAlgoOriginal) shadowed = in_shadow<ST, STATS, false>(c, hitW, regW);
+			else shadowed = h.laShadow ? in_shadow<ST, STATS, true>(c, hitW, regW) : in_shadow<ST, STATS, false>(c, hitW, regW);
+			return lit * (uint32_t)!shadowed;
+		}
+		rebase_region(o, reg);
+		ri = region_entry(c, p, reg);
+	}
+	return 0;
+}
+
+// calculateWorldRay (Renderer.cuh:1013-1022) + Camera::generateRay (Camera.cuh:25-29).  cam = 15 floats.
+VRM_HD void primary_ray(const float* cam, uint32_t x, uint32_t y, uint32_t W, uint32_t H, float* o, float* d)
+{
+	float u = vdiv(vadd((float)x, 0.5f), (float)W);
+	float v = vdiv(vadd((float)(H - y), 0.5f), (float)H);
+	float rel[3];
+	for (int i = 0; i < 3; i++)
+	{
+		o[i] = vadd(vadd(cam[3 + i], vmul(u, cam[6 + i])), vmul(v, cam[9 + i]));
+		rel[i] = vsub(o[i], cam[i]);
+	}
+	float len = vsqrt(vadd(vadd(vmul(rel[0], rel[0]), vmul(rel[1], rel[1])), vmul(rel[2], rel[2])));
+	d[0] = vdiv(rel[0], len); d[1] = vdiv(rel[1], len); d[2] = vdiv(rel[2], len);
+}
+
+}  // namespace vrm
