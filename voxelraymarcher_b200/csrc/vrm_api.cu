@@ -1,0 +1,334 @@
+// vrm_api.cu -- the extern "C" boundary declared in include/vrm_b200.h.
+#include "vrm_internal.h"
+#include "../../include/vrm_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+using namespace vrm;
+
+int vrm_fail_cuda(vrm_scene* s, cudaError_t e, const char* what)
+{
+	if (s) s->lastError = std::string(what) + ": " + cudaGetErrorString(e);
+	cudaGetLastError();  // clear the sticky-less error state
+	return e == cudaErrorMemoryAllocation ? VRM_ERR_NOMEM : VRM_ERR_CUDA;
+}
+
+namespace
+{
+
+int ensure(vrm_scene* s, void** p, size_t* have, size_t need)
+{
+	if (*have >= need && *p) return VRM_OK;
+	if (*p) { VRM_CUDA(s, cudaStreamSynchronize(s->stream)); cudaFree(*p); *p = nullptr; *have = 0; }
+	VRM_CUDA(s, cudaMalloc(p, need));
+	*have = need;
+	return VRM_OK;
+}
+
+int check_render_args(vrm_scene* s, const float* camera, const float* translation, int algorithm, uint32_t W, uint32_t H)
+{
+	if (!s) return VRM_ERR_INVALID;
+	if (s->storage < 0) { s->lastError = "scene not built"; return VRM_ERR_STATE; }
+	if (!camera || !translation || W == 0 || H == 0 || (algorithm != VRM_ALGO_ORIGINAL && algorithm != VRM_ALGO_LONGEST_AXIS))
+	{ s->lastError = "invalid render arguments"; return VRM_ERR_INVALID; }
+	return VRM_OK;
+}
+
+int upload_cameras(vrm_scene* s, const float* cameras, uint32_t nViews)
+{
+	size_t bytes = (size_t)nViews * VRM_CAMERA_FLOATS * sizeof(float);
+	if (s->camsBytes < bytes)
+	{
+		VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+		if (s->h_cams) cudaFreeHost(s->h_cams);
+		s->h_cams = nullptr;
+		VRM_CUDA(s, cudaMallocHost(&s->h_cams, bytes));
+		void* p = s->d_cams; size_t have = s->camsBytes;
+		int rc = ensure(s, &p, &have, bytes);
+		s->d_cams = static_cast<float*>(p); s->camsBytes = have;
+		if (rc) return rc;
+	}
+	else
+	{
+		// the pinned staging buffer may still be in flight from the previous asynchronous call
+		VRM_CUDA(s, cudaEventSynchronize(s->ev1));
+	}
+	memcpy(s->h_cams, cameras, bytes);
+	VRM_CUDA(s, cudaMemcpyAsync(s->d_cams, s->h_cams, bytes, cudaMemcpyHostToDevice, s->stream));
+	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+	return VRM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vrm_error_string(int status)
+{
+	switch (status)
+	{
+	case VRM_OK: return "ok";
+	case VRM_ERR_INVALID: return "invalid argument";
+	case VRM_ERR_CUDA: return "CUDA error";
+	case VRM_ERR_STATE: return "call not legal in this state";
+	case VRM_ERR_NOMEM: return "out of memory";
+	case VRM_ERR_BUILD: return "structure construction did not converge";
+	default: return "unknown status";
+	}
+}
+
+const char* vrm_last_error(const vrm_scene* scene) { return scene ? scene->lastError.c_str() : ""; }
+
+int vrm_device_available(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n > 0 ? 1 : 0;
+}
+
+int vrm_scene_create(int device, vrm_scene** out)
+{
+	if (!out) return VRM_ERR_INVALID;
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return VRM_ERR_CUDA; }  // no CPU fallback
+	if (device < 0 || device >= n) return VRM_ERR_INVALID;
+	vrm_scene* s = new (std::nothrow) vrm_scene();
+	if (!s) return VRM_ERR_NOMEM;
+	s->device = device;
+	// defaults = main/Main.cu:26-42
+	float inv[3] = {1.0f, 1.0f, 1.0f};
+	vrm_make_unit_vector(inv, s->light.dir);
+	s->light.color[0] = s->light.color[1] = s->light.color[2] = 1.0f;
+	s->light.pos[0] = 10.0f; s->light.pos[1] = 10.0f; s->light.pos[2] = -10.0f;
+	s->light.usePoint = 0; s->light.useShadows = 1;
+	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->ownStream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+	if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_stats, sizeof(Stats));
+	if (e == cudaSuccess) e = cudaMemset(s->d_stats, 0, sizeof(Stats));
+	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }
+	s->stream = s->ownStream;
+	cudaEventRecord(s->ev1, s->stream);
+	*out = s;
+	return VRM_OK;
+}
+
+int vrm_scene_destroy(vrm_scene* s)
+{
+	if (!s) return VRM_OK;
+	cudaSetDevice(s->device);
+	if (s->stream) cudaStreamSynchronize(s->stream);
+	for (VoxelChunk& c : s->chunks) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); }
+	vrm_free_structure(s);
+	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats);
+	if (s->h_cams) cudaFreeHost(s->h_cams);
+	if (s->ev0) cudaEventDestroy(s->ev0);
+	if (s->ev1) cudaEventDestroy(s->ev1);
+	if (s->ownStream) cudaStreamDestroy(s->ownStream);
+	cudaGetLastError();
+	delete s;
+	return VRM_OK;
+}
+
+int vrm_scene_set_stream(vrm_scene* s, void* cuda_stream)
+{
+	if (!s) return VRM_ERR_INVALID;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->ownStream;
+	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+	return VRM_OK;
+}
+
+int vrm_scene_synchronize(vrm_scene* s)
+{
+	if (!s) return VRM_ERR_INVALID;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	return VRM_OK;
+}
+
+static int add_voxels(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n, cudaMemcpyKind kind)
+{
+	if (!s || (n && (!xyz || !rgb))) return VRM_ERR_INVALID;
+	if (s->storage >= 0) { s->lastError = "scene already built"; return VRM_ERR_STATE; }
+	if (n == 0) return VRM_OK;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	VoxelChunk c = {nullptr, nullptr, n};
+	cudaError_t e = cudaMalloc(&c.d_xyz, n * 3 * sizeof(int32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&c.d_rgb, n * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMemcpyAsync(c.d_xyz, xyz, n * 3 * sizeof(int32_t), kind, s->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(c.d_rgb, rgb, n * sizeof(uint32_t), kind, s->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);  // the caller may reuse its buffers on return
+	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_add_voxels"); }
+	s->chunks.push_back(c);
+	s->nStaged += n;
+	return VRM_OK;
+}
+
+int vrm_scene_add_voxels(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n) { return add_voxels(s, xyz, rgb, n, cudaMemcpyHostToDevice); }
+int vrm_scene_add_voxels_device(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n) { return add_voxels(s, xyz, rgb, n, cudaMemcpyDeviceToDevice); }
+
+int vrm_scene_build(vrm_scene* s, int storage_type, float* build_ms)
+{
+	if (!s || (storage_type != VRM_STORAGE_VCS && storage_type != VRM_STORAGE_HASHTABLE)) return VRM_ERR_INVALID;
+	if (s->storage >= 0) { s->lastError = "scene already built"; return VRM_ERR_STATE; }
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	int rc = vrm_build_structure(s, storage_type, build_ms);
+	if (rc == VRM_OK)
+	{
+		// the staged copies are no longer needed
+		for (VoxelChunk& c : s->chunks) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); }
+		s->chunks.clear();
+	}
+	return rc;
+}
+
+int vrm_scene_info(const vrm_scene* s, uint32_t* diameter, int32_t* min_coord, uint32_t* filled, uint64_t* unique_voxels, uint64_t* bytes)
+{
+	if (!s) return VRM_ERR_INVALID;
+	if (s->storage < 0) return VRM_ERR_STATE;
+	if (diameter) *diameter = s->diameter;
+	if (min_coord) *min_coord = s->minCoord;
+	if (filled) *filled = s->filled;
+	if (unique_voxels) *unique_voxels = s->unique;
+	if (bytes) *bytes = s->bytes;
+	return VRM_OK;
+}
+
+int vrm_set_lighting(vrm_scene* s, const float direction[3], const float colour[3], const float position[3], int use_point_light, int use_shadows)
+{
+	if (!s || !direction || !colour || !position) return VRM_ERR_INVALID;
+	memcpy(s->light.dir, direction, 12); memcpy(s->light.color, colour, 12); memcpy(s->light.pos, position, 12);
+	s->light.usePoint = use_point_light != 0; s->light.useShadows = use_shadows != 0;
+	return VRM_OK;
+}
+
+int vrm_render_views_device(vrm_scene* s, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale, int algorithm,
+                            uint32_t width, uint32_t height, uint8_t* d_rgb_out, int32_t* d_hits_out)
+{
+	int rc = check_render_args(s, cameras, translation, algorithm, width, height);
+	if (rc) return rc;
+	if (!d_rgb_out || n_views == 0 || n_views > 65535) { s->lastError = "invalid render arguments"; return VRM_ERR_INVALID; }
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	rc = upload_cameras(s, cameras, n_views);
+	if (rc) return rc;
+	return vrm_launch_render(s, s->d_cams, n_views, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out);
+}
+
+int vrm_render_device(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float translation[3], uint32_t scale, int algorithm,
+                      uint32_t width, uint32_t height, uint8_t* d_rgb_out, int32_t* d_hits_out)
+{
+	return vrm_render_views_device(s, camera, 1, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out);
+}
+
+int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float translation[3], uint32_t scale, int algorithm,
+               uint32_t width, uint32_t height, uint8_t* rgb_out, int32_t* hits_out, float* kernel_ms)
+{
+	int rc = check_render_args(s, camera, translation, algorithm, width, height);
+	if (rc) return rc;
+	if (!rgb_out) { s->lastError = "rgb_out is NULL"; return VRM_ERR_INVALID; }
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	const size_t px = (size_t)width * height;
+	void* p = s->d_fb; rc = ensure(s, &p, &s->fbBytes, px * 3); s->d_fb = static_cast<uint8_t*>(p);
+	if (rc) return rc;
+	if (hits_out) { p = s->d_hits; rc = ensure(s, &p, &s->hitsBytes, px * 16); s->d_hits = static_cast<int32_t*>(p); if (rc) return rc; }
+	rc = upload_cameras(s, camera, 1);
+	if (rc) return rc;
+	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+	rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, s->d_fb, hits_out ? s->d_hits : nullptr);
+	if (rc) return rc;
+	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+	VRM_CUDA(s, cudaMemcpyAsync(rgb_out, s->d_fb, px * 3, cudaMemcpyDeviceToHost, s->stream));
+	if (hits_out) VRM_CUDA(s, cudaMemcpyAsync(hits_out, s->d_hits, px * 16, cudaMemcpyDeviceToHost, s->stream));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	if (kernel_ms) VRM_CUDA(s, cudaEventElapsedTime(kernel_ms, s->ev0, s->ev1));
+	return VRM_OK;
+}
+
+int vrm_trace_rays_device(vrm_scene* s, const float* d_rays, uint64_t n, const float translation[3], uint32_t scale, int algorithm,
+                          uint32_t* d_colour_out, int32_t* d_hits_out)
+{
+	if (!s) return VRM_ERR_INVALID;
+	if (s->storage < 0) { s->lastError = "scene not built"; return VRM_ERR_STATE; }
+	if ((n && (!d_rays || !d_colour_out)) || !translation || (algorithm != VRM_ALGO_ORIGINAL && algorithm != VRM_ALGO_LONGEST_AXIS))
+	{ s->lastError = "invalid trace arguments"; return VRM_ERR_INVALID; }
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	return vrm_launch_trace(s, d_rays, n, translation, scale, algorithm, d_colour_out, d_hits_out);
+}
+
+int vrm_trace_rays(vrm_scene* s, const float* rays, uint64_t n, const float translation[3], uint32_t scale, int algorithm,
+                   uint32_t* colour_out, int32_t* hits_out, float* kernel_ms)
+{
+	if (!s) return VRM_ERR_INVALID;
+	if (s->storage < 0) { s->lastError = "scene not built"; return VRM_ERR_STATE; }
+	if ((n && (!rays || !colour_out)) || !translation || (algorithm != VRM_ALGO_ORIGINAL && algorithm != VRM_ALGO_LONGEST_AXIS))
+	{ s->lastError = "invalid trace arguments"; return VRM_ERR_INVALID; }
+	if (kernel_ms) *kernel_ms = 0.0f;
+	if (n == 0) return VRM_OK;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	const size_t rayBytes = n * 24, colBytes = n * 4, hitBytes = hits_out ? n * 16 : 0;
+	int rc = ensure(s, &s->d_io, &s->ioBytes, rayBytes + colBytes + hitBytes);
+	if (rc) return rc;
+	char* base = static_cast<char*>(s->d_io);
+	int32_t* d_hits = hits_out ? reinterpret_cast<int32_t*>(base) : nullptr;  // 16-byte aligned first
+	float* d_rays = reinterpret_cast<float*>(base + hitBytes);
+	uint32_t* d_col = reinterpret_cast<uint32_t*>(base + hitBytes + rayBytes);
+	VRM_CUDA(s, cudaMemcpyAsync(d_rays, rays, rayBytes, cudaMemcpyHostToDevice, s->stream));
+	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+	rc = vrm_launch_trace(s, d_rays, n, translation, scale, algorithm, d_col, d_hits);
+	if (rc) return rc;
+	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+	VRM_CUDA(s, cudaMemcpyAsync(colour_out, d_col, colBytes, cudaMemcpyDeviceToHost, s->stream));
+	if (hits_out) VRM_CUDA(s, cudaMemcpyAsync(hits_out, d_hits, hitBytes, cudaMemcpyDeviceToHost, s->stream));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	if (kernel_ms) VRM_CUDA(s, cudaEventElapsedTime(kernel_ms, s->ev0, s->ev1));
+	return VRM_OK;
+}
+
+int vrm_lookup(vrm_scene* s, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* exists_out)
+{
+	if (!s || (n && (!xyz || !out))) return VRM_ERR_INVALID;
+	if (s->storage < 0) { s->lastError = "scene not built"; return VRM_ERR_STATE; }
+	if (n == 0) return VRM_OK;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	const size_t qBytes = n * 12, oBytes = n * 4, eBytes = n;
+	int rc = ensure(s, &s->d_io, &s->ioBytes, qBytes + oBytes + eBytes);
+	if (rc) return rc;
+	char* base = static_cast<char*>(s->d_io);
+	int32_t* d_q = reinterpret_cast<int32_t*>(base);
+	uint32_t* d_o = reinterpret_cast<uint32_t*>(base + qBytes);
+	uint8_t* d_e = reinterpret_cast<uint8_t*>(base + qBytes + oBytes);
+	VRM_CUDA(s, cudaMemcpyAsync(d_q, xyz, qBytes, cudaMemcpyHostToDevice, s->stream));
+	rc = vrm_launch_lookup(s, d_q, n, d_o, d_e);
+	if (rc) return rc;
+	VRM_CUDA(s, cudaMemcpyAsync(out, d_o, oBytes, cudaMemcpyDeviceToHost, s->stream));
+	if (exists_out) VRM_CUDA(s, cudaMemcpyAsync(exists_out, d_e, eBytes, cudaMemcpyDeviceToHost, s->stream));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	return VRM_OK;
+}
+
+int vrm_set_statistics(vrm_scene* s, int enabled)
+{
+	if (!s) return VRM_ERR_INVALID;
+	s->statsEnabled = enabled != 0;
+	return VRM_OK;
+}
+
+int vrm_get_statistics(vrm_scene* s, uint64_t out[8])
+{
+	if (!s || !out) return VRM_ERR_INVALID;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	Stats h;
+	VRM_CUDA(s, cudaMemcpyAsync(&h, s->d_stats, sizeof(Stats), cudaMemcpyDeviceToHost, s->stream));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	out[0] = h.nExist; out[1] = h.nExistFalse; out[2] = h.nLookup; out[3] = h.nLookupHit; out[4] = h.nProbe2; out[5] = h.nRegionReads;
+	out[6] = s->statsRays; out[7] = 0;
+	return VRM_OK;
+}
+
+}  // extern "C"

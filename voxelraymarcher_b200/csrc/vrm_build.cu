@@ -1,0 +1,505 @@
+// vrm_build.cu -- GPU construction of the two voxel storage structures (sm_100a).
+//
+// Replaces the reference's HOST builders:
+//   VoxelSceneCPU::insertVoxel / generateVoxelScene   geometry/VoxelSceneCPU.cuh:16-93   (std::unordered_map per region)
+//   CuckooHashTable ctor + createCuckooHashTable      storage/CuckooHashTable.cuh:20-49,97-178 (sequential eviction loop)
+//   VoxelClusterStore ctor                            storage/VoxelClusterStore.cuh:37-85 (bucket + std::sort per cluster)
+//   generateVoxelScene<<<1,1>>>                       renderer/Renderer.cuh:1066-1086    (serial device-side new)
+//
+// Pipeline (all on the handle's stream):
+//   1. region min/max reduction            -> minCoord, diameter           (VoxelSceneCPU.cuh:28-35,129-130)
+//   2. 64-bit key = regionIndex << 18 | clusterId << 9 | inClusterCode     (cluster-major order)
+//   3. stable LSD radix sort (8-bit digits, hand-written: histogram / scan / warp-match ranked scatter)
+//   4. last-write-wins dedupe (stable sort keeps insertion order inside an equal-key run; keep the run's last)
+//   5. region directory: dense region index per non-empty region, cubic table index ux + uy*D + uz*D*D
+//   6a. VCS: per cluster 16 x {32-bit occupancy mask, index of the word's first colour}; per region a 512-bit
+//       cluster-exists mask; colours stay in sorted order, so rank = popcount prefix (no binary search)
+//   6b. cuckoo: parallel insertion with 64-bit atomicExch eviction chains into per-region table pairs; regions whose
+//       chain bound is hit are cleared and re-inserted with fresh seeds (CuckooHashTable.cuh:118-129 does the same
+//       on the host with a 300 000-eviction bound).
+// Only key -> colour (last insert wins) and cluster occupancy are observable through the lookup seam, so the
+// layouts are free (SURVEY.md §7 hard part 4).
+#include "vrm_internal.h"
+#include "../../include/vrm_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+
+using namespace vrm;
+
+namespace
+{
+
+constexpr int kThreads = 256;
+constexpr int kSortItems = 8;                       // keys per thread in the radix passes
+constexpr int kSortTile = kThreads * kSortItems;    // 2048 keys per block
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kThreads * kScanItems;
+constexpr int kMaxEvictions = 400;
+constexpr int kMaxRebuilds = 24;
+
+struct DeviceBuf
+{
+	void* p = nullptr;
+	size_t bytes = 0;
+	~DeviceBuf() { if (p) cudaFree(p); }
+	cudaError_t alloc(size_t n) { bytes = n; return cudaMalloc(&p, n ? n : 16); }
+	template <class T> T* as() { return static_cast<T*>(p); }
+	void* release() { void* q = p; p = nullptr; return q; }
+};
+
+__device__ __forceinline__ int floor_div64(int v) { return v >> 6; }  // == floorf(v / 64.0f) for |v| < 2^24 (VoxelSceneCPU.cuh:19-21)
+
+// ---- 1. region extent ------------------------------------------------------------------------------------------
+__global__ void region_minmax_kernel(const int32_t* __restrict__ xyz, uint64_t n, int* __restrict__ minmax)
+{
+	int lo = 0, hi = 0;  // the reference initialises both to 0 (VoxelSceneCPU.cuh:129-130)
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n * 3; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		int r = floor_div64(xyz[i]);
+		lo = min(lo, r); hi = max(hi, r);
+	}
+	for (int o = 16; o; o >>= 1)
+	{
+		lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+		hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+	}
+	if ((threadIdx.x & 31) == 0) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
+}
+
+// ---- 2. keys ---------------------------------------------------------------------------------------------------
+__global__ void make_keys_kernel(const int32_t* __restrict__ xyz, const uint32_t* __restrict__ rgb, uint64_t n, uint64_t dstOffset,
+                                 int minCoord, uint32_t D, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+	int rx = floor_div64(x), ry = floor_div64(y), rz = floor_div64(z);
+	uint32_t lx = (uint32_t)(x & 63), ly = (uint32_t)(y & 63), lz = (uint32_t)(z & 63);  // ((c % 64) + 64) % 64, VoxelSceneCPU.cuh:24-26
+	unsigned long long region = ((unsigned long long)(uint32_t)(rz - minCoord) * D + (uint32_t)(ry - minCoord)) * D + (uint32_t)(rx - minCoord);
+	uint32_t cid = ((lx >> 3) << 6) | ((ly >> 3) << 3) | (lz >> 3);  // getVoxelClusterID, VoxelClusterStore.cuh:21-24
+	uint32_t code = ((lx & 7) << 6) | ((ly & 7) << 3) | (lz & 7);
+	keys[dstOffset + i] = (region << 18) | (cid << 9) | code;
+	vals[dstOffset + i] = rgb[i];
+}
+
+// ---- exclusive scan (uint32), recursive three-phase -----------------------------------------------------------------
+__global__ void scan_tile_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t* __restrict__ tileSums)
+{
+	__shared__ uint32_t warpSums[kThreads / 32];
+	uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+	uint32_t v[kScanItems];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++) { v[k] = base + k < n ? in[base + k] : 0u; sum += v[k]; }
+	uint32_t incl = sum;
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+	if (lane == 31) warpSums[warp] = incl;
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t w = lane < kThreads / 32 ? warpSums[lane] : 0u;
+		uint32_t wi = w;
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+		if (lane < kThreads / 32) warpSums[lane] = wi - w;
+		if (lane == kThreads / 32 - 1 && tileSums) tileSums[blockIdx.x] = wi;
+	}
+	__syncthreads();
+	uint32_t run = warpSums[warp] + incl - sum;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+
+__global__ void scan_add_kernel(uint32_t* __restrict__ out, uint64_t n, const uint32_t* __restrict__ tileOffsets)
+{
+	uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+	uint32_t add = tileOffsets[blockIdx.x];
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++) if (base + k < n) out[base + k] += add;
+}
+
+size_t scan_scratch_elems(uint64_t n)
+{
+	size_t total = 0;
+	while (n > (uint64_t)kScanTile) { n = (n + kScanTile - 1) / kScanTile; total += n; }
+	return total + 1;
+}
+
+// out may alias in.  scratch must hold scan_scratch_elems(n) uint32.
+void exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st)
+{
+	if (n == 0) return;
+	uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+	if (tiles == 1) { scan_tile_kernel<<<1, kThreads, 0, st>>>(in, out, n, nullptr); return; }
+	scan_tile_kernel<<<(unsigned)tiles, kThreads, 0, st>>>(in, out, n, scratch);
+	exclusive_scan(scratch, scratch, tiles, scratch + tiles, st);
+	scan_add_kernel<<<(unsigned)tiles, kThreads, 0, st>>>(out, n, scratch);
+}
+
+// ---- 3. radix sort ---------------------------------------------------------------------------------------------
+__global__ void radix_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n, int shift, uint32_t numTiles, uint32_t* __restrict__ hist)
+{
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++)
+	{
+		uint64_t i = base + (uint64_t)k * kThreads + threadIdx.x;
+		if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	hist[(uint64_t)threadIdx.x * numTiles + blockIdx.x] = h[threadIdx.x];  // digit-major so that one scan orders (digit, tile)
+}
+
+// Stable scatter: warp w of a tile owns keys [w*256, w*256+256) of the tile and walks them in rounds of 32 consecutive
+// keys, so (warp, round, lane) is the input order.  __match_any_sync groups equal digits inside a round.
+__global__ void radix_scatter_kernel(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, uint64_t n, int shift,
+                                     uint32_t numTiles, const uint32_t* __restrict__ histScanned,
+                                     unsigned long long* __restrict__ keysOut, uint32_t* __restrict__ valsOut)
+{
+	__shared__ uint32_t cnt[kThreads / 32][256];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < (kThreads / 32) * 256; i += kThreads) (&cnt[0][0])[i] = 0;
+	__syncthreads();
+	const uint64_t warpBase = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
+	unsigned long long key[kSortItems];
+	uint32_t rank[kSortItems];
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++)
+	{
+		uint64_t i = warpBase + (uint64_t)k * 32 + lane;
+		bool valid = i < n;
+		key[k] = valid ? keysIn[i] : 0ull;
+		uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & 255u) : 0xFFFFFFFFu;
+		uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+		int leader = __ffs(peers) - 1;
+		uint32_t before = __popc(peers & ((1u << lane) - 1u));
+		uint32_t prev = 0;
+		if (valid && lane == leader) { prev = cnt[warp][d]; cnt[warp][d] = prev + __popc(peers); }
+		prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+		rank[k] = prev + before;
+		__syncwarp();
+	}
+	__syncthreads();
+	{
+		// exclusive prefix over the warps of this tile, per digit; add the tile's global offset for the digit
+		uint32_t d = threadIdx.x;
+		uint32_t run = histScanned[(uint64_t)d * numTiles + blockIdx.x];
+		for (int w = 0; w < kThreads / 32; w++) { uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++)
+	{
+		uint64_t i = warpBase + (uint64_t)k * 32 + lane;
+		if (i < n)
+		{
+			uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
+			uint32_t dst = cnt[warp][d] + rank[k];
+			keysOut[dst] = key[k];
+			valsOut[dst] = valsIn[i];
+		}
+	}
+}
+
+// ---- 4. dedupe -------------------------------------------------------------------------------------------------
+__global__ void keep_last_kernel(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t* __restrict__ keep)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	keep[i] = (i + 1 == n || keys[i + 1] != keys[i]) ? 1u : 0u;  // last write wins, VoxelSceneCPU.cuh:45
+}
+
+__global__ void compact_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ keep,
+                               const uint32_t* __restrict__ pos, uint64_t n, unsigned long long* __restrict__ ukeys, uint32_t* __restrict__ uvals)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n || !keep[i]) return;
+	ukeys[pos[i]] = keys[i];
+	uvals[pos[i]] = vals[i];
+}
+
+// ---- 5. region directory ---------------------------------------------------------------------------------------
+__global__ void region_head_kernel(const unsigned long long* __restrict__ ukeys, uint64_t u, uint32_t* __restrict__ head)
+{
+	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (j >= u) return;
+	head[j] = (j == 0 || (ukeys[j] >> 18) != (ukeys[j - 1] >> 18)) ? 1u : 0u;
+}
+
+// headScan = exclusive scan of head.  regionOf[j] = dense region index of voxel j.
+__global__ void region_dir_kernel(const unsigned long long* __restrict__ ukeys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ headScan,
+                                  uint64_t u, int32_t* __restrict__ regionTable, uint32_t* __restrict__ regionStart, uint32_t* __restrict__ regionOf)
+{
+	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (j >= u) return;
+	uint32_t ri = headScan[j] + head[j] - 1u;
+	regionOf[j] = ri;
+	if (head[j])
+	{
+		regionTable[ukeys[j] >> 18] = (int32_t)ri;  // VoxelSceneCPU.cuh:61-62 (index), Renderer.cuh:1075 (entry)
+		regionStart[ri] = (uint32_t)j;
+	}
+}
+
+// ---- 6a. voxel cluster store -----------------------------------------------------------------------------------
+__global__ void vcs_fill_kernel(const unsigned long long* __restrict__ ukeys, const uint32_t* __restrict__ regionOf, uint64_t u,
+                                uint2* __restrict__ headers, uint32_t* __restrict__ clusterMask)
+{
+	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (j >= u) return;
+	unsigned long long k = ukeys[j];
+	uint32_t ri = regionOf[j];
+	uint32_t cid = (uint32_t)(k >> 9) & 511u, code = (uint32_t)k & 511u;
+	uint2* word = headers + ((size_t)ri * 512 + cid) * 16 + (code >> 5);
+	atomicOr(&word->x, 1u << (code & 31));
+	bool firstOfWord = j == 0 || (ukeys[j - 1] >> 5) != (k >> 5);
+	if (firstOfWord) word->y = (uint32_t)j;  // colours are sorted by (region, cluster, code): rank inside the word = popcount below the bit
+	bool firstOfCluster = j == 0 || (ukeys[j - 1] >> 9) != (k >> 9);
+	if (firstOfCluster) atomicOr(clusterMask + (size_t)ri * 16 + (cid >> 5), 1u << (cid & 31));
+}
+
+// ---- 6b. cuckoo hash table -------------------------------------------------------------------------------------
+__global__ void fill_slots_kernel(unsigned long long* __restrict__ slots, uint64_t n)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) slots[i] = kEmptySlot;
+}
+
+__global__ void clear_failed_regions_kernel(unsigned long long* __restrict__ slots, const HashRegionDesc* __restrict__ desc, const uint32_t* __restrict__ retry, uint32_t numRegions)
+{
+	// one block per region
+	uint32_t ri = blockIdx.x;
+	if (ri >= numRegions || !retry[ri]) return;
+	HashRegionDesc d = desc[ri];
+	for (uint32_t i = threadIdx.x; i < 2 * d.n; i += blockDim.x) slots[(size_t)d.slotBase + i] = kEmptySlot;
+}
+
+__global__ void cuckoo_insert_kernel(const unsigned long long* __restrict__ ukeys, const uint32_t* __restrict__ uvals, const uint32_t* __restrict__ regionOf, uint64_t u,
+                                     const HashRegionDesc* __restrict__ desc, unsigned long long* __restrict__ slots,
+                                     const uint32_t* __restrict__ retry /* nullable: insert everything */, uint32_t* __restrict__ failed)
+{
+	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (j >= u) return;
+	uint32_t ri = regionOf[j];
+	if (retry && !retry[ri]) return;
+	HashRegionDesc d = desc[ri];
+	unsigned long long k = ukeys[j];
+	uint32_t cid = (uint32_t)(k >> 9) & 511u, code = (uint32_t)k & 511u;
+	uint32_t x = ((cid >> 6) << 3) | (code >> 6), y = (((cid >> 3) & 7u) << 3) | ((code >> 3) & 7u), z = ((cid & 7u) << 3) | (code & 7u);
+	unsigned long long entry = ((unsigned long long)((x << 12) | (y << 6) | z) << 32) | uvals[j];
+	unsigned long long* t1 = slots + d.slotBase;
+	unsigned long long* t2 = t1 + d.n;
+	int table = 0;
+	for (int it = 0; it < kMaxEvictions; it++)
+	{
+		uint32_t key = (uint32_t)(entry >> 32);
+		unsigned long long* slot = table == 0 ? t1 + hash_slot1(key, d.seed1, d.n) : t2 + hash_slot2(key, d.seed2, d.n);
+		entry = atomicExch(slot, entry);  // evict whoever lives there (CuckooHashTable.cuh:137-151), atomically
+		if (entry == kEmptySlot) return;
+		table ^= 1;                       // the evicted entry moves to its other table
+	}
+	failed[ri] = 1u;  // cycle bound hit: the region is rebuilt with new hash seeds (CuckooHashTable.cuh:118-129)
+}
+
+uint32_t seed_for(uint32_t ri, uint32_t attempt, uint32_t which)
+{
+	uint32_t h = ri * 0x9E3779B1u + attempt * 0x85EBCA77u + which * 0xC2B2AE3Du + 0x27D4EB2Fu;
+	h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+	return h;
+}
+
+unsigned grid_for(uint64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+void vrm_free_structure(vrm_scene* s)
+{
+	cudaFree(s->d_regionTable); s->d_regionTable = nullptr;
+	cudaFree(s->d_hashDesc); s->d_hashDesc = nullptr;
+	cudaFree(s->d_slots); s->d_slots = nullptr;
+	cudaFree(s->d_headers); s->d_headers = nullptr;
+	cudaFree(s->d_clusterMask); s->d_clusterMask = nullptr;
+	cudaFree(s->d_values); s->d_values = nullptr;
+	s->storage = -1; s->bytes = 0; s->filled = 0; s->unique = 0;
+}
+
+int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
+{
+	cudaStream_t st = s->stream;
+	const uint64_t n = s->nStaged;
+	if (n >= (1ull << 32) - (uint64_t)kSortTile) { s->lastError = "too many voxels for 32-bit indices"; return VRM_ERR_INVALID; }
+	VRM_CUDA(s, cudaEventRecord(s->ev0, st));
+
+	// 1. extent
+	DeviceBuf minmax;
+	VRM_CUDA(s, minmax.alloc(2 * sizeof(int)));
+	VRM_CUDA(s, cudaMemsetAsync(minmax.p, 0, 2 * sizeof(int), st));
+	for (const VoxelChunk& c : s->chunks)
+		if (c.n) region_minmax_kernel<<<(unsigned)std::min<uint64_t>((c.n * 3 + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(c.d_xyz, c.n, minmax.as<int>());
+	int hostMinMax[2] = {0, 0};
+	VRM_CUDA(s, cudaMemcpyAsync(hostMinMax, minmax.p, sizeof(hostMinMax), cudaMemcpyDeviceToHost, st));
+	VRM_CUDA(s, cudaStreamSynchronize(st));
+	const int minCoord = hostMinMax[0];
+	const uint64_t D = (uint64_t)(hostMinMax[1] - hostMinMax[0] + 1);
+	if (D > 1024) { s->lastError = "region table diameter > 1024 (scene spans more than 65536 voxels)"; return VRM_ERR_INVALID; }
+	const uint64_t tableSize = D * D * D;
+	int regionBits = 0;
+	while ((1ull << regionBits) < tableSize) regionBits++;
+	const int keyBits = 18 + regionBits;
+
+	DeviceBuf regionTable;
+	if (regionTable.alloc(tableSize * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); s->lastError = "region table allocation failed"; return VRM_ERR_NOMEM; }
+	VRM_CUDA(s, cudaMemsetAsync(regionTable.p, 0xFF, tableSize * sizeof(int32_t), st));  // -1 = empty region (the reference forgets to clear this)
+
+	uint64_t unique = 0;
+	uint32_t numRegions = 0;
+	DeviceBuf ukeys, uvals, regionOf, regionStart;
+	if (n > 0)
+	{
+		// 2. keys
+		DeviceBuf keysA, keysB, valsA, valsB, hist, scratch;
+		const uint32_t numTiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+		const uint64_t histElems = 256ull * numTiles;
+		if (keysA.alloc(n * 8) != cudaSuccess || keysB.alloc(n * 8) != cudaSuccess || valsA.alloc(n * 4) != cudaSuccess || valsB.alloc(n * 4) != cudaSuccess ||
+		    hist.alloc(histElems * 4) != cudaSuccess || scratch.alloc(scan_scratch_elems(std::max<uint64_t>(histElems, n)) * 4) != cudaSuccess)
+		{ cudaGetLastError(); s->lastError = "sort buffer allocation failed"; return VRM_ERR_NOMEM; }
+		uint64_t off = 0;
+		for (const VoxelChunk& c : s->chunks)
+		{
+			if (!c.n) continue;
+			make_keys_kernel<<<grid_for(c.n), kThreads, 0, st>>>(c.d_xyz, c.d_rgb, c.n, off, minCoord, (uint32_t)D, keysA.as<unsigned long long>(), valsA.as<uint32_t>());
+			off += c.n;
+		}
+		// 3. stable LSD radix sort
+		unsigned long long* kin = keysA.as<unsigned long long>(); unsigned long long* kout = keysB.as<unsigned long long>();
+		uint32_t* vin = valsA.as<uint32_t>(); uint32_t* vout = valsB.as<uint32_t>();
+		for (int shift = 0; shift < keyBits; shift += 8)
+		{
+			radix_hist_kernel<<<numTiles, kThreads, 0, st>>>(kin, n, shift, numTiles, hist.as<uint32_t>());
+			exclusive_scan(hist.as<uint32_t>(), hist.as<uint32_t>(), histElems, scratch.as<uint32_t>(), st);
+			radix_scatter_kernel<<<numTiles, kThreads, 0, st>>>(kin, vin, n, shift, numTiles, hist.as<uint32_t>(), kout, vout);
+			std::swap(kin, kout); std::swap(vin, vout);
+		}
+		// 4. dedupe (kout / vout are free now: reuse vout as the keep flags, hist is too small -> allocate pos)
+		DeviceBuf pos;
+		if (pos.alloc(n * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "dedupe buffer allocation failed"; return VRM_ERR_NOMEM; }
+		uint32_t* keep = vout;
+		keep_last_kernel<<<grid_for(n), kThreads, 0, st>>>(kin, n, keep);
+		exclusive_scan(keep, pos.as<uint32_t>(), n, scratch.as<uint32_t>(), st);
+		uint32_t lastPos = 0, lastKeep = 0;
+		VRM_CUDA(s, cudaMemcpyAsync(&lastPos, pos.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+		VRM_CUDA(s, cudaMemcpyAsync(&lastKeep, keep + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+		VRM_CUDA(s, cudaStreamSynchronize(st));
+		unique = (uint64_t)lastPos + lastKeep;
+		if (ukeys.alloc(unique * 8) != cudaSuccess || uvals.alloc(unique * 4) != cudaSuccess || regionOf.alloc(unique * 4) != cudaSuccess)
+		{ cudaGetLastError(); s->lastError = "unique voxel allocation failed"; return VRM_ERR_NOMEM; }
+		compact_kernel<<<grid_for(n), kThreads, 0, st>>>(kin, vin, keep, pos.as<uint32_t>(), n, ukeys.as<unsigned long long>(), uvals.as<uint32_t>());
+		// 5. region directory (reuse pos / keep as head-scan / head flags: unique <= n)
+		uint32_t* head = keep;
+		uint32_t* headScan = pos.as<uint32_t>();
+		region_head_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), unique, head);
+		exclusive_scan(head, headScan, unique, scratch.as<uint32_t>(), st);
+		uint32_t lastScan = 0, lastHead = 0;
+		VRM_CUDA(s, cudaMemcpyAsync(&lastScan, headScan + (unique - 1), 4, cudaMemcpyDeviceToHost, st));
+		VRM_CUDA(s, cudaMemcpyAsync(&lastHead, head + (unique - 1), 4, cudaMemcpyDeviceToHost, st));
+		VRM_CUDA(s, cudaStreamSynchronize(st));
+		numRegions = lastScan + lastHead;
+		if (regionStart.alloc(((size_t)numRegions + 1) * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "region directory allocation failed"; return VRM_ERR_NOMEM; }
+		region_dir_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), head, headScan, unique, regionTable.as<int32_t>(),
+		                                                          regionStart.as<uint32_t>(), regionOf.as<uint32_t>());
+		uint32_t u32 = (uint32_t)unique;
+		VRM_CUDA(s, cudaMemcpyAsync(regionStart.as<uint32_t>() + numRegions, &u32, 4, cudaMemcpyHostToDevice, st));
+		VRM_CUDA(s, cudaStreamSynchronize(st));  // keep/pos/scratch (and &u32) go out of scope below
+		VRM_CUDA(s, cudaGetLastError());
+	}
+
+	uint64_t bytes = tableSize * sizeof(int32_t);
+	DeviceBuf headers, clusterMask, hashDesc, slots;
+	if (storageType == VRM_STORAGE_VCS)
+	{
+		const size_t headerBytes = (size_t)numRegions * 512 * 16 * sizeof(uint2);
+		if (headers.alloc(headerBytes) != cudaSuccess || clusterMask.alloc((size_t)numRegions * 16 * 4) != cudaSuccess)
+		{ cudaGetLastError(); s->lastError = "VCS allocation failed"; return VRM_ERR_NOMEM; }
+		VRM_CUDA(s, cudaMemsetAsync(headers.p, 0, headerBytes, st));
+		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4, st));
+		if (unique)
+			vcs_fill_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), regionOf.as<uint32_t>(), unique, headers.as<uint2>(), clusterMask.as<uint32_t>());
+		VRM_CUDA(s, cudaGetLastError());
+		bytes += headerBytes + (size_t)numRegions * 64 + unique * 4;
+	}
+	else
+	{
+		std::vector<uint32_t> starts((size_t)numRegions + 1, 0);
+		if (numRegions) VRM_CUDA(s, cudaMemcpyAsync(starts.data(), regionStart.p, starts.size() * 4, cudaMemcpyDeviceToHost, st));
+		VRM_CUDA(s, cudaStreamSynchronize(st));
+		std::vector<HashRegionDesc> desc(numRegions);
+		uint64_t totalSlots = 0;
+		for (uint32_t r = 0; r < numRegions; r++)
+		{
+			uint32_t cnt = starts[r + 1] - starts[r];
+			desc[r].n = cnt + cnt / 4 + 2;  // 1.25 N slots per table as in the reference (CuckooHashTable.cuh:23), +2 so tiny regions can always place
+			desc[r].slotBase = (uint32_t)totalSlots;
+			desc[r].seed1 = seed_for(r, 0, 1); desc[r].seed2 = seed_for(r, 0, 2);
+			totalSlots += 2ull * desc[r].n;
+		}
+		if (totalSlots >= (1ull << 32)) { s->lastError = "hash table needs more than 2^32 slots"; return VRM_ERR_INVALID; }
+		DeviceBuf failed, retry;
+		if (hashDesc.alloc((size_t)numRegions * sizeof(HashRegionDesc)) != cudaSuccess || slots.alloc(totalSlots * 8) != cudaSuccess ||
+		    failed.alloc((size_t)numRegions * 4) != cudaSuccess || retry.alloc((size_t)numRegions * 4) != cudaSuccess)
+		{ cudaGetLastError(); s->lastError = "hash table allocation failed"; return VRM_ERR_NOMEM; }
+		if (numRegions)
+		{
+			VRM_CUDA(s, cudaMemcpyAsync(hashDesc.p, desc.data(), desc.size() * sizeof(HashRegionDesc), cudaMemcpyHostToDevice, st));
+			fill_slots_kernel<<<148 * 8, kThreads, 0, st>>>(slots.as<unsigned long long>(), totalSlots);
+			std::vector<uint32_t> hostFailed(numRegions);
+			bool all = true;
+			int attempt = 0;
+			for (;; attempt++)
+			{
+				VRM_CUDA(s, cudaMemsetAsync(failed.p, 0, (size_t)numRegions * 4, st));
+				cuckoo_insert_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), uvals.as<uint32_t>(), regionOf.as<uint32_t>(), unique,
+				                                                           hashDesc.as<HashRegionDesc>(), slots.as<unsigned long long>(), all ? nullptr : retry.as<uint32_t>(), failed.as<uint32_t>());
+				VRM_CUDA(s, cudaMemcpyAsync(hostFailed.data(), failed.p, (size_t)numRegions * 4, cudaMemcpyDeviceToHost, st));
+				VRM_CUDA(s, cudaStreamSynchronize(st));
+				bool any = false;
+				for (uint32_t r = 0; r < numRegions; r++)
+					if (hostFailed[r]) { any = true; desc[r].seed1 = seed_for(r, attempt + 1, 1); desc[r].seed2 = seed_for(r, attempt + 1, 2); }
+				if (!any) break;
+				if (attempt + 1 >= kMaxRebuilds) { s->lastError = "cuckoo insertion did not converge"; return VRM_ERR_BUILD; }
+				VRM_CUDA(s, cudaMemcpyAsync(hashDesc.p, desc.data(), desc.size() * sizeof(HashRegionDesc), cudaMemcpyHostToDevice, st));
+				VRM_CUDA(s, cudaMemcpyAsync(retry.p, hostFailed.data(), (size_t)numRegions * 4, cudaMemcpyHostToDevice, st));
+				clear_failed_regions_kernel<<<numRegions, kThreads, 0, st>>>(slots.as<unsigned long long>(), hashDesc.as<HashRegionDesc>(), retry.as<uint32_t>(), numRegions);
+				all = false;
+			}
+			VRM_CUDA(s, cudaGetLastError());
+		}
+		bytes += (size_t)numRegions * sizeof(HashRegionDesc) + totalSlots * 8;
+	}
+	VRM_CUDA(s, cudaEventRecord(s->ev1, st));
+	VRM_CUDA(s, cudaStreamSynchronize(st));
+	VRM_CUDA(s, cudaGetLastError());
+	if (buildMs) VRM_CUDA(s, cudaEventElapsedTime(buildMs, s->ev0, s->ev1));
+
+	s->d_regionTable = static_cast<int32_t*>(regionTable.release());
+	if (storageType == VRM_STORAGE_VCS)
+	{
+		s->d_headers = static_cast<uint2*>(headers.release());
+		s->d_clusterMask = static_cast<uint32_t*>(clusterMask.release());
+		s->d_values = static_cast<uint32_t*>(uvals.release());
+	}
+	else
+	{
+		s->d_hashDesc = static_cast<HashRegionDesc*>(hashDesc.release());
+		s->d_slots = static_cast<unsigned long long*>(slots.release());
+	}
+	s->storage = storageType;
+	s->diameter = (uint32_t)D;
+	s->minCoord = minCoord;
+	s->filled = numRegions;
+	s->unique = unique;
+	s->bytes = bytes;
+	return VRM_OK;
+}

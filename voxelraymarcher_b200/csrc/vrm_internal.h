@@ -1,0 +1,84 @@
+// vrm_internal.h -- state behind the opaque vrm_scene handle (host side).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "vrm_core.cuh"
+
+struct VoxelChunk
+{
+	int32_t* d_xyz;
+	uint32_t* d_rgb;
+	uint64_t n;
+};
+
+struct vrm_scene
+{
+	int device = 0;
+	cudaStream_t ownStream = nullptr;
+	cudaStream_t stream = nullptr;
+	std::string lastError;
+
+	// staged voxels (insertion order)
+	std::vector<VoxelChunk> chunks;
+	uint64_t nStaged = 0;
+
+	// built structure
+	int storage = -1;
+	uint32_t diameter = 0;
+	int32_t minCoord = 0;
+	uint32_t filled = 0;
+	uint64_t unique = 0;
+	uint64_t bytes = 0;
+	int32_t* d_regionTable = nullptr;
+	vrm::HashRegionDesc* d_hashDesc = nullptr;
+	unsigned long long* d_slots = nullptr;
+	uint2* d_headers = nullptr;
+	uint32_t* d_clusterMask = nullptr;
+	uint32_t* d_values = nullptr;
+
+	vrm::Lighting light;
+
+	// scratch owned by the handle for the host-buffer entry points
+	uint8_t* d_fb = nullptr;     size_t fbBytes = 0;
+	int32_t* d_hits = nullptr;   size_t hitsBytes = 0;
+	float* d_cams = nullptr;     size_t camsBytes = 0;
+	float* h_cams = nullptr;     // pinned staging for cameras
+	void* d_io = nullptr;        size_t ioBytes = 0;   // rays / lookup queries and results
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+	bool statsEnabled = false;
+	vrm::Stats* d_stats = nullptr;
+	uint64_t statsRays = 0;
+
+	vrm::SceneView view() const
+	{
+		vrm::SceneView v;
+		v.regionTable = d_regionTable; v.diameter = diameter; v.minCoord = minCoord;
+		v.hashDesc = d_hashDesc; v.slots = d_slots;
+		v.headers = d_headers; v.clusterMask = d_clusterMask; v.values = d_values;
+		return v;
+	}
+};
+
+// status helpers -------------------------------------------------------------------------------------------------
+int vrm_fail_cuda(vrm_scene* s, cudaError_t e, const char* what);
+#define VRM_CUDA(s, call)                                                   \
+	do {                                                                    \
+		cudaError_t e__ = (call);                                           \
+		if (e__ != cudaSuccess) return vrm_fail_cuda((s), e__, #call);      \
+	} while (0)
+
+// vrm_build.cu
+int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs);
+void vrm_free_structure(vrm_scene* s);
+
+// vrm_render.cu
+int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits);
+int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float* translation, uint32_t scale, int algorithm,
+                     uint32_t* d_colour, int32_t* d_hits);
+int vrm_launch_lookup(vrm_scene* s, const int32_t* d_xyz, uint64_t n, uint32_t* d_out, uint8_t* d_exists);

@@ -1,0 +1,215 @@
+// vrm_render.cu -- render / trace / lookup kernels (sm_100a).  Replaces rayMarchSceneOriginal and
+// rayMarchSceneJumpAxis (renderer/Renderer.cuh:1033-1063) and their launch (main/Main.cu:105-163).
+//
+// One thread per pixel; a warp owns an 8x4 pixel tile (coherent primary rays: neighbouring pixels walk the same
+// clusters, so their lookups share 128-byte lines), a 256-thread CTA owns a 32x8 block of pixels, blockIdx.z is the
+// view.  Storage type and algorithm are template parameters: four specialised kernels instead of the reference's two
+// kernels with virtual storage dispatch (the specialisation the reference's own dead OptimizedFunctions.cuh aimed at).
+// Compile with -fmad=false as a second line of defence; the core already spells every float op with *_rn intrinsics.
+#include "vrm_internal.h"
+#include "../../include/vrm_b200.h"
+
+using namespace vrm;
+
+namespace
+{
+
+constexpr int kTileW = 8, kTileH = 4;          // pixels per warp
+constexpr int kBlockTilesX = 4, kBlockTilesY = 2;
+constexpr int kBlockW = kTileW * kBlockTilesX;  // 32
+constexpr int kBlockH = kTileH * kBlockTilesY;  // 8
+constexpr int kRenderThreads = kBlockW * kBlockH;
+
+struct RenderArgs
+{
+	SceneView sv;
+	Lighting light;
+	float translation[3];
+	float scale;
+	const float* cams;  // nViews x 15
+	uint32_t W, H;
+	uint8_t* rgb;       // nViews x H x W x 3
+	int32_t* hits;      // nullable, nViews x H x W x 4
+	Stats* stats;       // nullable
+};
+
+template <bool STATS, int ST>
+__device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* out)
+{
+	if constexpr (STATS)
+	{
+		unsigned long long v[6] = {c.st.nExist, c.st.nExistFalse, c.st.nLookup, c.st.nLookupHit, c.st.nProbe2, c.st.nRegionReads};
+#pragma unroll
+		for (int k = 0; k < 6; k++)
+		{
+			unsigned long long x = v[k];
+			for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+			if ((threadIdx.x & 31) == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(out) + k, x);
+		}
+	}
+}
+
+template <int ST, int ALGO, bool STATS>
+__global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderArgs a)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t x = blockIdx.x * kBlockW + (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1));
+	const uint32_t y = blockIdx.y * kBlockH + (warp / kBlockTilesX) * kTileH + (lane / kTileW);
+	const bool inside = x < a.W && y < a.H;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	if (inside)
+	{
+		const float* cam = a.cams + (size_t)blockIdx.z * 15;
+		float camv[15];
+#pragma unroll
+		for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+		float o[3], d[3];
+		primary_ray(camv, x, y, a.W, a.H, o, d);
+		uint32_t color = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
+		// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
+		a.rgb[3 * p] = (uint8_t)(color >> 16);
+		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
+		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
+		if (a.hits) reinterpret_cast<int4*>(a.hits)[p] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+	}
+	flush_stats<STATS>(c, a.stats);
+}
+
+struct TraceArgs
+{
+	SceneView sv;
+	Lighting light;
+	float translation[3];
+	float scale;
+	const float* rays;  // n x 6
+	unsigned long long n;
+	uint32_t* colour;
+	int32_t* hits;
+	Stats* stats;
+};
+
+template <int ST, int ALGO, bool STATS>
+__global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
+{
+	unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	if (i < a.n)
+	{
+		float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
+		float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
+		a.colour[i] = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+		if (a.hits) reinterpret_cast<int4*>(a.hits)[i] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+	}
+	flush_stats<STATS>(c, a.stats);
+}
+
+// The storage seam on global voxel coordinates (StorageStructure.cuh:12-17).
+template <int ST>
+__global__ void lookup_kernel(SceneView sv, const int32_t* __restrict__ xyz, unsigned long long n, uint32_t* __restrict__ out, uint8_t* __restrict__ exists)
+{
+	unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	RayCtx<ST, false> c;
+	c.sv = sv;
+	c.reset();
+	PermIdentity p;
+	int v[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+	int reg[3] = {v[0] >> 6, v[1] >> 6, v[2] >> 6};   // floor(c / 64), VoxelSceneCPU.cuh:19-21
+	int l[3] = {v[0] & 63, v[1] & 63, v[2] & 63};     // VoxelSceneCPU.cuh:24-26
+	uint32_t res = kEmpty;
+	uint8_t e = 0;
+	int32_t ri = region_entry(c, p, reg);
+	if (ri >= 0)
+	{
+		RegionRef<ST> r = load_region<ST>(sv, ri);
+		e = space_exists(c, r, p, l[0], l[1], l[2]) ? 1 : 0;
+		if (e) res = lookup_voxel(c, r, p, reg, l[0], l[1], l[2]);
+	}
+	out[i] = res;
+	if (exists) exists[i] = e;
+}
+
+template <class Args> void fill_common(Args& a, const vrm_scene* s, const float* translation, uint32_t scale)
+{
+	a.sv = s->view();
+	a.light = s->light;
+	a.translation[0] = translation[0]; a.translation[1] = translation[1]; a.translation[2] = translation[2];
+	a.scale = static_cast<float>(scale);  // Ray.cuh:16
+	a.stats = s->statsEnabled ? s->d_stats : nullptr;
+}
+
+template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs& a, dim3 grid)
+{
+	if (s->statsEnabled) render_kernel<ST, ALGO, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+	else render_kernel<ST, ALGO, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+}
+
+template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a, unsigned grid)
+{
+	if (s->statsEnabled) trace_kernel<ST, ALGO, true><<<grid, 256, 0, s->stream>>>(a);
+	else trace_kernel<ST, ALGO, false><<<grid, 256, 0, s->stream>>>(a);
+}
+
+}  // namespace
+
+int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits)
+{
+	RenderArgs a;
+	fill_common(a, s, translation, scale);
+	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
+	if (s->statsEnabled)
+	{
+		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
+		s->statsRays = (uint64_t)W * H * nViews;
+	}
+	dim3 grid((W + kBlockW - 1) / kBlockW, (H + kBlockH - 1) / kBlockH, nViews);
+	const bool hash = s->storage == VRM_STORAGE_HASHTABLE, orig = algorithm == VRM_ALGO_ORIGINAL;
+	if (hash && orig) launch_render_t<kStorageHash, kAlgoOriginal>(s, a, grid);
+	else if (hash) launch_render_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
+	else if (orig) launch_render_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
+	else launch_render_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
+	VRM_CUDA(s, cudaGetLastError());
+	return VRM_OK;
+}
+
+int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float* translation, uint32_t scale, int algorithm,
+                     uint32_t* d_colour, int32_t* d_hits)
+{
+	if (n == 0) return VRM_OK;
+	TraceArgs a;
+	fill_common(a, s, translation, scale);
+	a.rays = d_rays; a.n = n; a.colour = d_colour; a.hits = d_hits;
+	if (s->statsEnabled)
+	{
+		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
+		s->statsRays = n;
+	}
+	unsigned grid = (unsigned)((n + 255) / 256);
+	const bool hash = s->storage == VRM_STORAGE_HASHTABLE, orig = algorithm == VRM_ALGO_ORIGINAL;
+	if (hash && orig) launch_trace_t<kStorageHash, kAlgoOriginal>(s, a, grid);
+	else if (hash) launch_trace_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
+	else if (orig) launch_trace_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
+	else launch_trace_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
+	VRM_CUDA(s, cudaGetLastError());
+	return VRM_OK;
+}
+
+int vrm_launch_lookup(vrm_scene* s, const int32_t* d_xyz, uint64_t n, uint32_t* d_out, uint8_t* d_exists)
+{
+	if (n == 0) return VRM_OK;
+	unsigned grid = (unsigned)((n + 255) / 256);
+	if (s->storage == VRM_STORAGE_HASHTABLE) lookup_kernel<kStorageHash><<<grid, 256, 0, s->stream>>>(s->view(), d_xyz, n, d_out, d_exists);
+	else lookup_kernel<kStorageVcs><<<grid, 256, 0, s->stream>>>(s->view(), d_xyz, n, d_out, d_exists);
+	VRM_CUDA(s, cudaGetLastError());
+	return VRM_OK;
+}
