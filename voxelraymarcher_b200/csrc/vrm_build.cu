@@ -252,12 +252,20 @@ __global__ void vcs_fill_kernel(const unsigned long long* __restrict__ ukeys, co
 	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if (j >= u) return;
 	unsigned long long k = ukeys[j];
+	// The voxels of one 32-bit occupancy word are contiguous in the sorted array: its first voxel owns the word and
+	// gathers the (at most 32) bits itself -- no atomics, no contention on the densely filled words of solid terrain.
+	if (j != 0 && (ukeys[j - 1] >> 5) == (k >> 5)) return;
 	uint32_t ri = regionOf[j];
 	uint32_t cid = (uint32_t)(k >> 9) & 511u, code = (uint32_t)k & 511u;
-	uint2* word = headers + ((size_t)ri * 512 + cid) * 16 + (code >> 5);
-	atomicOr(&word->x, 1u << (code & 31));
-	bool firstOfWord = j == 0 || (ukeys[j - 1] >> 5) != (k >> 5);
-	if (firstOfWord) word->y = (uint32_t)j;  // colours are sorted by (region, cluster, code): rank inside the word = popcount below the bit
+	uint32_t mask = 1u << (code & 31);
+	for (uint64_t t = j + 1; t < u && t < j + 32; t++)
+	{
+		unsigned long long kt = ukeys[t];
+		if ((kt >> 5) != (k >> 5)) break;
+		mask |= 1u << ((uint32_t)kt & 31);
+	}
+	// colours are sorted by (region, cluster, code): rank inside the word = popcount below the bit
+	headers[((size_t)ri * 512 + cid) * 16 + (code >> 5)] = make_uint2(mask, (uint32_t)j);
 	bool firstOfCluster = j == 0 || (ukeys[j - 1] >> 9) != (k >> 9);
 	if (firstOfCluster) atomicOr(clusterMask + (size_t)ri * 16 + (cid >> 5), 1u << (cid & 31));
 }
