@@ -6,9 +6,8 @@ scene at 1/2/4/8 B200).
     python bench.py --impl reference ...                      (the reference's own CPU implementation on the host cores)
 
 A step = one pass of the hot path over one batch of synthetic input = ONE 3840x2160 frame per GPU of the procedural
-512^3 terrain (~32 M voxels, BASELINE.json configs[2]) with the reference's default CLI combination
-(Voxel Cluster Store + longest-axis traversal, Main.cu:45-68), camera on an orbit (a different view every step and
-rank), shadows on.  The voxel structure is built once per GPU, on the GPU, before the timed region and is replicated
+512^3 terrain (~32 M voxels, BASELINE.json configs[2]: "single view") with the reference's default CLI combination
+(Voxel Cluster Store + longest-axis traversal, Main.cu:45-68), SURVEY.md 8d-3's camera, shadows on.  The voxel structure is built once per GPU, on the GPU, before the timed region and is replicated
 on every rank; at N>1 every step ends with the NCCL gather of the finished frames on rank 0 (the path's only
 exchange step), so `value` includes it.
 
@@ -139,7 +138,7 @@ def run_reference_arm(args, rank, world):
     ref = po.OracleScene(kind)
     ref.add_voxels(xyz, rgb)
     ref.build(STORAGE)
-    cams = [po.make_camera(*_orbit_args(v), kind) for v in range(args.warmup + args.steps)]
+    cams = [po.make_camera(*_orbit_args(0), kind) for v in range(args.warmup + args.steps)]
     for i in range(args.warmup):
         ref.render(cams[i], WIDTH, HEIGHT, ALGORITHM, want_hits=False, threads=cores)
     t0 = time.perf_counter()
@@ -168,8 +167,8 @@ def _orbit_args(view):
 def workload_config():
     return {"workload": f"terrain{SCENE_SIZE}_4k_{STORAGE}_{ALGORITHM}", "scene": f"procedural {SCENE_SIZE}^3 terrain, seed {SCENE_SEED}, ~32 M voxels (BASELINE.json configs[2])",
             "resolution": f"{WIDTH}x{HEIGHT}", "storage": STORAGE, "algorithm": ALGORITHM, "shadows": True,
-            "views": f"{ORBIT_VIEWS}-view orbit, one view per GPU per step", "l2": "flushed between steps (512 MiB write, outside the per-step event pairs)",
-            "parallelism": "views sharded across GPUs, structure replicated, NCCL gather of frames to rank 0"}
+            "views": "one frame per GPU per step, camera (-96,352,-96) -> (256,64,256), fov 60 (SURVEY.md 8d-3)", "l2": "flushed between steps (512 MiB write, outside the per-step event pairs)",
+            "parallelism": "frames sharded across GPUs (one per GPU per step), structure replicated, NCCL gather of frames to rank 0"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -208,14 +207,15 @@ def main():
     scene.add_voxels(xyz, rgb)
     build_ms = scene.generate_voxel_scene(STORAGE)
     info = scene.info()
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # a dedicated non-default stream: kernels, flushes, NCCL ordering and events all live here
+    torch.cuda.set_stream(stream)
     scene.set_stream(stream.cuda_stream)
 
     frame = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev)
     gathered = [torch.zeros_like(frame) for _ in range(world)] if (world > 1 and rank == 0) else None
     flush = torch.zeros(512 << 20, dtype=torch.uint8, device=dev)
     total = args.warmup + args.steps
-    cams = [orbit_camera(api, (i * world + rank)) for i in range(total)]
+    cams = [orbit_camera(api, 0) for i in range(total)]   # configs[2] is a single view: every rank renders SURVEY.md §8d-3's camera
 
     def step(i, ev0, ev1, evk):
         flush.add_(1)                       # evict L2 (512 MiB > 126 MB), not timed
@@ -330,13 +330,14 @@ def baseline_legs(api, scene, xyz, rgb, cam, flush, dev):
             scenes_by_storage[storage] = s
         s = scenes_by_storage[storage]
         fb = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev)
-        s.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        cur = torch.cuda.current_stream(dev)
+        s.set_stream(cur.cuda_stream)
         for algo in ("longestaxis", "original"):
             times = []
             for i in range(9):
                 flush.add_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); s.render_device(WIDTH, HEIGHT, algo, cam, fb.data_ptr()); e1.record()
+                e0.record(cur); s.render_device(WIDTH, HEIGHT, algo, cam, fb.data_ptr()); e1.record(cur)
                 torch.cuda.synchronize(dev)
                 if i >= 2:
                     times.append(e0.elapsed_time(e1))

@@ -65,9 +65,11 @@ int vrm_device_available(void);
 int vrm_scene_create(int device, vrm_scene** out);
 int vrm_scene_destroy(vrm_scene* scene);
 
-/* Use a caller-provided cudaStream_t (passed as void*) for all later work of this handle; NULL restores the
- * handle's own stream.  Lets a host framework time the kernels with its own events. */
+/* Use a caller-provided cudaStream_t (passed as void*; 0 is CUDA's legacy default stream) for all later work of this
+ * handle, so that a host framework can order and time the kernels with its own events.  vrm_scene_reset_stream goes
+ * back to the handle's own non-blocking stream. */
 int vrm_scene_set_stream(vrm_scene* scene, void* cuda_stream);
+int vrm_scene_reset_stream(vrm_scene* scene);
 int vrm_scene_synchronize(vrm_scene* scene);
 
 /* Append voxels in insertion order: xyz = n x 3 int32, rgb = n x uint32 (r<<16|g<<8|b).  Duplicate coordinates:

@@ -30,7 +30,7 @@ EMPTY = 1 << 30                                # EMPTY_KEY / EMPTY_VAL
 
 EXPORTS = [
     "vrm_error_string", "vrm_last_error", "vrm_device_available", "vrm_scene_create", "vrm_scene_destroy",
-    "vrm_scene_set_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
+    "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
     "vrm_set_statistics", "vrm_get_statistics",
@@ -61,6 +61,7 @@ def load_library():
         "vrm_scene_create": (ci, [ci, C.POINTER(vp)]),
         "vrm_scene_destroy": (ci, [vp]),
         "vrm_scene_set_stream": (ci, [vp, vp]),
+        "vrm_scene_reset_stream": (ci, [vp]),
         "vrm_scene_synchronize": (ci, [vp]),
         "vrm_scene_add_voxels": (ci, [vp, vp, vp, u64]),
         "vrm_scene_add_voxels_device": (ci, [vp, vp, vp, u64]),
@@ -158,8 +159,12 @@ class VoxelScene:
         except Exception:
             pass
 
-    def set_stream(self, cuda_stream_ptr: int | None):
-        self._check(self.lib.vrm_scene_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)), "vrm_scene_set_stream")
+    def set_stream(self, cuda_stream_ptr: int):
+        """Run on the caller's cudaStream_t (0 = the legacy default stream)."""
+        self._check(self.lib.vrm_scene_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "vrm_scene_set_stream")
+
+    def reset_stream(self):
+        self._check(self.lib.vrm_scene_reset_stream(self.h), "vrm_scene_reset_stream")
 
     def synchronize(self):
         self._check(self.lib.vrm_scene_synchronize(self.h), "vrm_scene_synchronize")

@@ -139,7 +139,17 @@ int vrm_scene_set_stream(vrm_scene* s, void* cuda_stream)
 	if (!s) return VRM_ERR_INVALID;
 	VRM_CUDA(s, cudaSetDevice(s->device));
 	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
-	s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->ownStream;
+	s->stream = static_cast<cudaStream_t>(cuda_stream);
+	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+	return VRM_OK;
+}
+
+int vrm_scene_reset_stream(vrm_scene* s)
+{
+	if (!s) return VRM_ERR_INVALID;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	s->stream = s->ownStream;
 	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
 	return VRM_OK;
 }
