@@ -61,6 +61,9 @@ const char* vrm_error_string(int status);
 const char* vrm_last_error(const vrm_scene* scene);
 /* 1 when a CUDA device is usable in this process, else 0. */
 int vrm_device_available(void);
+/* pickCudaDevice, main/Main.cu:82-94: number of CUDA devices (0 when none) and a device's name. */
+int vrm_device_count(void);
+int vrm_device_name(int device, char* out, uint64_t capacity);
 
 int vrm_scene_create(int device, vrm_scene** out);
 int vrm_scene_destroy(vrm_scene* scene);

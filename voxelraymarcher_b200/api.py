@@ -29,7 +29,7 @@ ALGORITHM = {"longestaxis": ALGO_LONGEST_AXIS, "original": ALGO_ORIGINAL}
 EMPTY = 1 << 30                                # EMPTY_KEY / EMPTY_VAL
 
 EXPORTS = [
-    "vrm_error_string", "vrm_last_error", "vrm_device_available", "vrm_scene_create", "vrm_scene_destroy",
+    "vrm_error_string", "vrm_last_error", "vrm_device_available", "vrm_device_count", "vrm_device_name", "vrm_scene_create", "vrm_scene_destroy",
     "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
@@ -58,6 +58,8 @@ def load_library():
         "vrm_error_string": (C.c_char_p, [ci]),
         "vrm_last_error": (C.c_char_p, [vp]),
         "vrm_device_available": (ci, []),
+        "vrm_device_count": (ci, []),
+        "vrm_device_name": (ci, [ci, C.c_char_p, u64]),
         "vrm_scene_create": (ci, [ci, C.POINTER(vp)]),
         "vrm_scene_destroy": (ci, [vp]),
         "vrm_scene_set_stream": (ci, [vp, vp]),

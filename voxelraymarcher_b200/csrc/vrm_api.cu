@@ -88,6 +88,24 @@ int vrm_device_available(void)
 	return n > 0 ? 1 : 0;
 }
 
+int vrm_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int vrm_device_name(int device, char* out, uint64_t capacity)
+{
+	if (!out || capacity == 0) return VRM_ERR_INVALID;
+	out[0] = 0;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	strncpy(out, prop.name, capacity - 1);
+	out[capacity - 1] = 0;
+	return VRM_OK;
+}
+
 int vrm_scene_create(int device, vrm_scene** out)
 {
 	if (!out) return VRM_ERR_INVALID;
