@@ -15,6 +15,7 @@ struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 
 #include "../../voxelraymarcher_b200/csrc/vrm_core.cuh"
+#include "../../voxelraymarcher_b200/csrc/vrm_flat.cuh"
 
 using namespace vrm;
 
@@ -45,6 +46,13 @@ struct SimScene
 };
 
 Lighting gLight = {{0.57735026f, 0.57735026f, 0.57735026f}, {1, 1, 1}, {10, 10, -10}, 0, 1};
+int gFlat = 1;  // 1: the flat state machine of vrm_flat.cuh (what the render kernels run); 0: the nested form of vrm_core.cuh
+
+template <int ST, int ALGO>
+uint32_t march(RayCtx<ST, true>& c, const float* o, const float* d, float scale)
+{
+	return gFlat ? march_scene_flat<ST, ALGO, true>(c, o, d, scale) : march_scene<ST, ALGO, true>(c, o, d, scale);
+}
 
 int floordiv64(int v) { return v >= 0 ? v / 64 : -((-v + 63) / 64); }
 
@@ -65,7 +73,7 @@ void render_rows(const SimScene& s, const float* cam, const float* tr, float sca
 				float o[3], d[3];
 				c.reset();
 				primary_ray(cam, x, (uint32_t)y, W, H, o, d);
-				uint32_t color = march_scene<ST, ALGO, true>(c, o, d, scale);
+				uint32_t color = march<ST, ALGO>(c, o, d, scale);
 				size_t p = (size_t)y * W + x;
 				rgb[3 * p] = (uint8_t)(color >> 16); rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF); rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
 				if (hits) memcpy(hits + 4 * p, c.hit, 16);
@@ -96,7 +104,7 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 		for (int64_t i = 0; i < (int64_t)n; i++)
 		{
 			c.reset();
-			colour[i] = march_scene<ST, ALGO, true>(c, rays + 6 * i, rays + 6 * i + 3, scale);
+			colour[i] = march<ST, ALGO>(c, rays + 6 * i, rays + 6 * i + 3, scale);
 			if (hits) memcpy(hits + 4 * i, c.hit, 16);
 			local[0] += c.st.nExist; local[1] += c.st.nExistFalse; local[2] += c.st.nLookup; local[3] += c.st.nLookupHit;
 			if (c.st.nLookup > local[4]) local[4] = c.st.nLookup;
@@ -114,6 +122,7 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 
 extern "C" {
 
+void sim_set_flat(int flat) { gFlat = flat; }
 void* sim_scene_create() { return new SimScene(); }
 void sim_scene_destroy(void* h) { delete static_cast<SimScene*>(h); }
 

@@ -3,6 +3,7 @@
 #include "../../include/vrm_b200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -128,6 +129,9 @@ int vrm_scene_create(int device, vrm_scene** out)
 	if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_stats, sizeof(Stats));
 	if (e == cudaSuccess) e = cudaMemset(s->d_stats, 0, sizeof(Stats));
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_queue, sizeof(unsigned int));
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->numSms, cudaDevAttrMultiProcessorCount, device);
+	if (const char* mode = getenv("VRM_RENDER_MODE")) s->renderMode = atoi(mode);
 	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }
 	s->stream = s->ownStream;
 	cudaEventRecord(s->ev1, s->stream);
@@ -142,7 +146,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (VoxelChunk& c : s->chunks) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); }
 	vrm_free_structure(s);
-	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats);
+	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue);
 	if (s->h_cams) cudaFreeHost(s->h_cams);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);

@@ -50,6 +50,10 @@ struct vrm_scene
 	void* d_io = nullptr;        size_t ioBytes = 0;   // rays / lookup queries and results
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
+	int numSms = 148;
+	int renderMode = 0;               // 0 = flat state machine + persistent ray queue; 1 = nested form (VRM_RENDER_MODE=1, A/B only)
+
 	bool statsEnabled = false;
 	vrm::Stats* d_stats = nullptr;
 	uint64_t statsRays = 0;

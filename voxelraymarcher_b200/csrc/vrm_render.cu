@@ -7,6 +7,7 @@
 // kernels with virtual storage dispatch (the specialisation the reference's own dead OptimizedFunctions.cuh aimed at).
 // Compile with -fmad=false as a second line of defence; the core already spells every float op with *_rn intrinsics.
 #include "vrm_internal.h"
+#include "vrm_flat.cuh"
 #include "../../include/vrm_b200.h"
 
 using namespace vrm;
@@ -31,6 +32,8 @@ struct RenderArgs
 	uint8_t* rgb;       // nViews x H x W x 3
 	int32_t* hits;      // nullable, nViews x H x W x 4
 	Stats* stats;       // nullable
+	unsigned int* queue;   // persistent kernel: next unclaimed pixel slot
+	uint32_t tilesX, tilesPerView, nViews;
 };
 
 template <bool STATS, int ST>
@@ -80,6 +83,83 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderArgs
 	flush_stats<STATS>(c, a.stats);
 }
 
+// ---- persistent-thread ray queue -----------------------------------------------------------------------------------
+// Pixel slots are numbered tile-major: slot = (view * tilesPerView + tile) * 32 + pixel-in-8x4-tile, so that 32 consecutive
+// slots are one warp-coherent tile.  Every lane runs FlatRay micro-steps; when at least kRefillLanes lanes of a warp have
+// resolved their pixel (or all have), the idle lanes claim the next slots with ONE warp-aggregated atomicAdd and start new
+// primary rays, so divergent ray lengths no longer leave most of a warp idle until its slowest ray finishes.
+constexpr int kPersistThreads = 128;
+constexpr int kRefillLanes = 8;
+
+template <int ST, int ALGO, bool STATS>
+__global__ void __launch_bounds__(kPersistThreads) render_persistent_kernel(const RenderArgs a)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned total = a.nViews * a.tilesPerView * 32u;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	FlatRay<ST, ALGO, STATS> ray;
+	ray.st = kStDone;
+	size_t pixel = 0;
+	bool exhausted = false;  // warp-uniform: the queue has run dry
+	for (;;)
+	{
+		const bool idle = ray.st == kStDone;
+		const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, idle);
+		if (idleMask == 0xFFFFFFFFu && exhausted) break;
+		if (!exhausted && (idleMask == 0xFFFFFFFFu || __popc(idleMask) >= kRefillLanes))
+		{
+			const int want = __popc(idleMask);
+			const int leader = __ffs(idleMask) - 1;
+			unsigned base = 0;
+			if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned)want);
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (base + want >= total) exhausted = true;
+			if (idle)
+			{
+				const unsigned slot = base + __popc(idleMask & ((1u << lane) - 1u));
+				if (slot < total)
+				{
+					const unsigned tile = slot >> 5, inTile = slot & 31u;
+					const unsigned view = tile / a.tilesPerView, t = tile - view * a.tilesPerView;
+					const uint32_t x = (t % a.tilesX) * kTileW + (inTile & (kTileW - 1));
+					const uint32_t y = (t / a.tilesX) * kTileH + (inTile / kTileW);
+					if (x < a.W && y < a.H)
+					{
+						const float* cam = a.cams + (size_t)view * 15;
+						float camv[15];
+#pragma unroll
+						for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+						float o[3], d[3];
+						primary_ray(camv, x, y, a.W, a.H, o, d);
+						c.hit[0] = c.hit[1] = c.hit[2] = c.hit[3] = 0;
+						pixel = ((size_t)view * a.H + y) * a.W + x;
+						ray.start_primary(c, o, d, a.scale);
+						if (ray.st == kStDone)  // missed the scene's bounding cube altogether
+						{
+							a.rgb[3 * pixel] = 0; a.rgb[3 * pixel + 1] = 0; a.rgb[3 * pixel + 2] = 0;
+							if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(0, 0, 0, 0);
+						}
+					}
+				}
+			}
+		}
+		if (ray.st != kStDone && ray.step(c))
+		{
+			const uint32_t color = ray.result;
+			// writeColorToFramebuffer, Renderer.cuh:1024-1031
+			a.rgb[3 * pixel] = (uint8_t)(color >> 16);
+			a.rgb[3 * pixel + 1] = (uint8_t)((color >> 8) & 0xFF);
+			a.rgb[3 * pixel + 2] = (uint8_t)(color & 0xFF);
+			if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+		}
+	}
+	flush_stats<STATS>(c, a.stats);
+}
+
 struct TraceArgs
 {
 	SceneView sv;
@@ -106,7 +186,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 	{
 		float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
 		float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
-		a.colour[i] = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+		a.colour[i] = march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale);
 		if (a.hits) reinterpret_cast<int4*>(a.hits)[i] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 	}
 	flush_stats<STATS>(c, a.stats);
@@ -149,8 +229,25 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 
 template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs& a, dim3 grid)
 {
-	if (s->statsEnabled) render_kernel<ST, ALGO, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-	else render_kernel<ST, ALGO, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+	if (s->renderMode == 1)  // nested form, one CTA per 32x8 pixels (kept for A/B measurements: VRM_RENDER_MODE=1)
+	{
+		if (s->statsEnabled) render_kernel<ST, ALGO, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		else render_kernel<ST, ALGO, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		return;
+	}
+	// persistent kernel: as many CTAs as fit on the device at once (a multiple of the SM count)
+	static int blocksPerSm[2][2][2] = {};
+	int& bps = blocksPerSm[ST][ALGO][s->statsEnabled ? 1 : 0];
+	if (bps == 0)
+	{
+		if (s->statsEnabled) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_persistent_kernel<ST, ALGO, true>, kPersistThreads, 0);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_persistent_kernel<ST, ALGO, false>, kPersistThreads, 0);
+		if (bps < 1) bps = 1;
+	}
+	const unsigned blocks = (unsigned)(s->numSms * bps);
+	cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned int), s->stream);
+	if (s->statsEnabled) render_persistent_kernel<ST, ALGO, true><<<blocks, kPersistThreads, 0, s->stream>>>(a);
+	else render_persistent_kernel<ST, ALGO, false><<<blocks, kPersistThreads, 0, s->stream>>>(a);
 }
 
 template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a, unsigned grid)
@@ -167,6 +264,11 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	RenderArgs a;
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
+	a.queue = s->d_queue;
+	a.tilesX = (W + kTileW - 1) / kTileW;
+	a.tilesPerView = a.tilesX * ((H + kTileH - 1) / kTileH);
+	a.nViews = nViews;
+	if ((uint64_t)a.tilesPerView * nViews * 32ull >= (1ull << 32)) { s->lastError = "too many pixels for one launch"; return VRM_ERR_INVALID; }
 	if (s->statsEnabled)
 	{
 		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
