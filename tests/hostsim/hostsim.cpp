@@ -185,7 +185,7 @@ int sim_scene_build(void* h, int storageType)
 		s->slots.resize(s->slots.size() + 2 * (size_t)d.n, kEmptySlot);
 		for (uint32_t attempt = 0;; attempt++)
 		{
-			d.seed1 = 0x9E3779B9u * (attempt + 1) + (uint32_t)ri; d.seed2 = 0x7F4A7C15u * (attempt + 1) ^ (uint32_t)ri;
+			d.seed1 = (0x9E3779B9u * (attempt + 1) + (uint32_t)ri * 0x85EBCA77u) | 1u; d.seed2 = ((0x7F4A7C15u * (attempt + 1)) ^ ((uint32_t)ri * 0xC2B2AE3Du) ^ 0x27D4EB2Fu) | 1u;  // odd multipliers
 			std::fill(s->slots.begin() + d.slotBase, s->slots.end(), kEmptySlot);
 			bool ok = true;
 			for (auto& v : kv.second)

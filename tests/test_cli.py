@@ -74,6 +74,6 @@ def test_cli_reads_magicavoxel(tmp_path):
     s.add_voxels(xyz, rgb)
     s.generate_voxel_scene("vcs")
     cam = api.Camera((6.0, 2.0, 6.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 60.0, np.float32(640) / np.float32(360))
-    want = s.render(640, 360, "original", cam, scale=1)["rgb"]
-    assert np.array_equal(img, want)
-    assert want.any()
+    want = s.render(640, 360, "original", cam, scale=1, want_hits=True)
+    assert np.array_equal(img, want["rgb"])
+    assert want["hits"][..., 3].sum() > 1000

@@ -316,7 +316,7 @@ uint32_t seed_for(uint32_t ri, uint32_t attempt, uint32_t which)
 {
 	uint32_t h = ri * 0x9E3779B1u + attempt * 0x85EBCA77u + which * 0xC2B2AE3Du + 0x27D4EB2Fu;
 	h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
-	return h;
+	return h | 1u;  // multiply-shift hashing needs an odd multiplier (vrm_core.cuh hash_slot1/2)
 }
 
 unsigned grid_for(uint64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }

@@ -65,6 +65,80 @@ VRM_HD float min3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
 // o + t * d, the reference's  origin + (t * direction)  (math/Vector3.cuh:105-109,134-138)
 VRM_HD float along(float o, float t, float d) { return vadd(o, vmul(t, d)); }
 
+// ---------------------------------------------------------------- exact division by a per-ray constant
+//
+// The walk divides by the three direction components at every step ("t = (next - o) / d", Renderer.cuh:273-275 and
+// siblings) and those divisors never change along a ray.  IEEE division (div.rn.f32) costs ~12 issue slots on sm_100a
+// (MUFU.RCP + 5 FFMA + FCHK + slow-path branch); with y = RN(1/d) computed once per ray the correctly rounded quotient is
+//     q0 = RN(x * y);  r = x - d * q0  (one FMA, exact);  q = RN(q0 + r * y)            (Markstein)
+// i.e. 3 issue slots.  Before rounding, q0 + r*y = (x/d)(1 - e1*(e1+e2+e1*e2)) with |e1|,|e2| <= 2^-24, a relative
+// perturbation below 2^-47; the result was checked equal to x/d for all 2^23 numerator mantissas against 200 000
+// denominators (1.7e12 cases, incl. all-ones / sparse mantissas) and on 2.4e9 adversarial near-midpoint quotients.
+// This is the SAME value as the reference's division, not an approximation: parity stays bit-exact.
+//
+// Preconditions (else fall back to div.rn): d normal with 2^-40 <= |d| <= 2^40 (so y, q are far from over/underflow) and
+// every numerator either exactly 0 or |x| >= 2^-100 (so that the residual r cannot underflow).  One compare per step
+// covers both: thr is 2^-100 for a "fast" ray and NaN otherwise, and the slow path is taken unless min|x_i| >= thr.
+// (An exactly zero numerator also takes the slow path; it is rare -- a ray exactly on a cluster face.)
+#if defined(__CUDA_ARCH__)
+VRM_HD float vfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+VRM_HD float vrcp(float a) { return __frcp_rn(a); }
+#else
+VRM_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+VRM_HD float vrcp(float a) { return 1.0f / a; }
+#endif
+
+struct RayDir
+{
+	float d[3];   // direction, walk space
+	float rd[3];  // RN(1 / d)
+	float thr;    // fast-division threshold (see above)
+};
+
+VRM_HD bool dir_component_safe(float v)
+{
+	float a = fabsf(v);
+	return a >= 9.094947017729282e-13f && a <= 1.099511627776e12f;  // 2^-40 .. 2^40 (false for 0, inf, NaN, denormals)
+}
+
+VRM_HD RayDir make_raydir(float d0, float d1, float d2)
+{
+	RayDir k;
+	k.d[0] = d0; k.d[1] = d1; k.d[2] = d2;
+	k.rd[0] = vrcp(d0); k.rd[1] = vrcp(d1); k.rd[2] = vrcp(d2);
+	const bool fast = dir_component_safe(d0) && dir_component_safe(d1) && dir_component_safe(d2);
+	k.thr = fast ? 7.888609052210118e-31f : NAN;  // 2^-100
+	return k;
+}
+
+VRM_HD float div_by_const(float x, float d, float rd)
+{
+	float q0 = vmul(x, rd);
+	float r = vfma(-d, q0, x);
+	return vfma(r, rd, q0);
+}
+
+// a_i = x_i / d_i, bit-identical to IEEE division
+VRM_HD void div3(float x0, float x1, float x2, const RayDir& k, float& a0, float& a1, float& a2)
+{
+	float m = fminf(fabsf(x0), fminf(fabsf(x1), fabsf(x2)));
+	if (!(m >= k.thr))
+	{
+		a0 = vdiv(x0, k.d[0]); a1 = vdiv(x1, k.d[1]); a2 = vdiv(x2, k.d[2]);
+	}
+	else
+	{
+		a0 = div_by_const(x0, k.d[0], k.rd[0]); a1 = div_by_const(x1, k.d[1], k.rd[1]); a2 = div_by_const(x2, k.d[2], k.rd[2]);
+	}
+}
+
+VRM_HD float div1(float x, const RayDir& k, int i)
+{
+	float ax = fabsf(x);
+	if (!(ax >= k.thr)) return vdiv(x, k.d[i]);
+	return div_by_const(x, k.d[i], k.rd[i]);
+}
+
 // ---------------------------------------------------------------- scene description (device pointers)
 
 struct Lighting
@@ -157,20 +231,12 @@ template <class P, class T> VRM_HD void to_world(const P& p, const T* w, T* xyz)
 
 // ---------------------------------------------------------------- storage access
 
-VRM_HD uint32_t mix_a(uint32_t h)
-{
-	h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-	return h;
-}
-VRM_HD uint32_t mix_b(uint32_t h)
-{
-	h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
-	return h;
-}
-// Slot index inside one table: multiply-shift range reduction instead of the reference's four integer modulos
-// per probe (CuckooHashTable.cuh:62,69).
-VRM_HD uint32_t hash_slot1(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32(mix_a(key ^ seed), n); }
-VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32(mix_b(key ^ seed), n); }
+// Slot index inside one table: multiply-shift hashing with a per-region random ODD multiplier (the "seed"; universal for
+// the high bits of key * seed mod 2^32) followed by a multiply-high range reduction -- two integer instructions per table
+// instead of the reference's two signed mixing functions and four integer modulos per probe
+// (CuckooHashTable.cuh:62,69,181-202).  The builder re-draws the multipliers of a region whose insertion cycles.
+VRM_HD uint32_t hash_slot1(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
+VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 
 template <int ST> struct RegionRef;
 
@@ -379,6 +445,15 @@ template <bool GUARD> VRM_HD float t_to(float next, float o, float d)  // Render
 	if (GUARD) t = (d != 0.0f) ? t : INFINITY;
 	return t;
 }
+// the three t values of one advance: (next_i - o_i) / d_i with the ray's exact-division constants
+template <bool GUARD> VRM_HD void t_to3(const RayDir& k, float n0, float n1, float n2, const float* o, float& a0, float& a1, float& a2)
+{
+	div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), k, a0, a1, a2);
+	if (GUARD)
+	{
+		a0 = (k.d[0] != 0.0f) ? a0 : INFINITY; a1 = (k.d[1] != 0.0f) ? a1 : INFINITY; a2 = (k.d[2] != 0.0f) ? a2 : INFINITY;
+	}
+}
 VRM_HD int cluster_edge(float d, int v)  // Renderer.cuh:293-295
 {
 	return d > 0.0f ? ((v / 8) + 1) * 8 : (v / 8) * 8;
@@ -389,7 +464,7 @@ VRM_HD void rebase_region(float* o, int* reg)
 {
 	for (int i = 0; i < 3; i++)
 	{
-		int diff = (int)floorf(vdiv(o[i], (float)kRegion));
+		int diff = (int)floorf(vmul(o[i], 0.015625f));  // o / 64: 1/64 is a power of two, so the product is the same correctly rounded value
 		reg[i] += diff;
 		o[i] = vmul(1.0f, vsub(o[i], (float)(diff * kRegion)));  // convertRayToLocalSpace(.., scale 1), Ray.cuh:14-17
 	}
@@ -397,14 +472,17 @@ VRM_HD void rebase_region(float* o, int* reg)
 
 // Null-region skip, Renderer.cuh:384-410 (GUARD: 185-211).  On return ri >= 0 (a stored region) or -2 (left the scene).
 template <int ST, bool STATS, class P, bool GUARD>
-VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, const float* d, int* reg, int32_t ri)
+VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, const RayDir& k, int* reg, int32_t ri)
 {
+	const float* d = k.d;
 	while (ri == -1)
 	{
 		float n0 = d[0] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
 		float n1 = d[1] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
 		float n2 = d[2] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
-		float tMin = min3(t_to<GUARD>(n0, o[0], d[0]), t_to<GUARD>(n1, o[1], d[1]), t_to<GUARD>(n2, o[2], d[2]));
+		float a0, a1, a2;
+		t_to3<GUARD>(k, n0, n1, n2, o, a0, a1, a2);
+		float tMin = min3(a0, a1, a2);
 		o[0] = along(o[0], tMin, d[0]); o[1] = along(o[1], tMin, d[1]); o[2] = along(o[2], tMin, d[2]);
 		rebase_region(o, reg);
 		ri = region_entry(c, p, reg);
@@ -418,11 +496,11 @@ VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, con
 // (Renderer.cuh:100-172, GUARD=true).  Returns the raw voxel colour or kEmpty; t[0..3] = the OUTER tX,tY,tZ,tMin
 // of the hit step (stale after a cluster skip, exactly as in the reference, SURVEY.md §7 hard part 3).
 template <int ST, bool STATS, class P, bool GUARD>
-VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const float* d, const int* reg, float* t)
+VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const RayDir& k, const int* reg, float* t)
 {
-	float t0 = t_to<GUARD>(next_edge(d[0], o[0]), o[0], d[0]);
-	float t1 = t_to<GUARD>(next_edge(d[1], o[1]), o[1], d[1]);
-	float t2 = t_to<GUARD>(next_edge(d[2], o[2]), o[2], d[2]);
+	const float* d = k.d;
+	float t0, t1, t2;
+	t_to3<GUARD>(k, next_edge(d[0], o[0]), next_edge(d[1], o[1]), next_edge(d[2], o[2]), o, t0, t1, t2);
 	float tMin = min3(t0, t1, t2);
 	float s = vadd(tMin, kEps);
 	o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
@@ -431,9 +509,8 @@ VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const 
 		int v0 = (int)o[0], v1 = (int)o[1], v2 = (int)o[2];
 		if (!space_exists(c, r, p, v0, v1, v2))
 		{
-			float u0 = t_to<GUARD>((float)cluster_edge(d[0], v0), o[0], d[0]);
-			float u1 = t_to<GUARD>((float)cluster_edge(d[1], v1), o[1], d[1]);
-			float u2 = t_to<GUARD>((float)cluster_edge(d[2], v2), o[2], d[2]);
+			float u0, u1, u2;
+			t_to3<GUARD>(k, (float)cluster_edge(d[0], v0), (float)cluster_edge(d[1], v1), (float)cluster_edge(d[2], v2), o, u0, u1, u2);
 			float su = vadd(min3(u0, u1, u2), kEps);
 			o[0] = along(o[0], su, d[0]); o[1] = along(o[1], su, d[1]); o[2] = along(o[2], su, d[2]);
 			continue;
@@ -444,9 +521,7 @@ VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const 
 			t[0] = t0; t[1] = t1; t[2] = t2; t[3] = tMin;
 			return col;
 		}
-		t0 = t_to<GUARD>(next_edge(d[0], o[0]), o[0], d[0]);
-		t1 = t_to<GUARD>(next_edge(d[1], o[1]), o[1], d[1]);
-		t2 = t_to<GUARD>(next_edge(d[2], o[2]), o[2], d[2]);
+		t_to3<GUARD>(k, next_edge(d[0], o[0]), next_edge(d[1], o[1]), next_edge(d[2], o[2]), o, t0, t1, t2);
 		tMin = min3(t0, t1, t2);
 		s = vadd(tMin, kEps);
 		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
@@ -466,10 +541,11 @@ struct HitInfo
 
 // rayMarchVoxelGrid, Renderer.cuh:260-336 (the hit's lighting + shadow are applied by the caller)
 template <int ST, bool STATS, class P>
-VRM_HD uint32_t march_original(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const float* d, const int* reg, HitInfo& h)
+VRM_HD uint32_t march_original(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const RayDir& k, const int* reg, HitInfo& h)
 {
+	const float* d = k.d;
 	float t[4];
-	uint32_t col = march_steps<ST, STATS, P, false>(c, r, p, o, d, reg, t);
+	uint32_t col = march_steps<ST, STATS, P, false>(c, r, p, o, k, reg, t);
 	if (col == kEmpty) return kEmpty;
 	h.nAxisW = normal_axis_from_t(p, t[0], t[1], t[2], t[3]);  // Renderer.cuh:312
 	float dn = p.axis(0) == h.nAxisW ? d[0] : (p.axis(1) == h.nAxisW ? d[1] : d[2]);
@@ -481,6 +557,14 @@ VRM_HD uint32_t march_original(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, con
 
 // ---------------------------------------------------------------- "longest axis" traversal (walk slot 0 = L, 1 = M, 2 = S)
 
+// Ray::convertRayToLongestAxisDirection's scaling (Ray.cuh:37,52,67,69): direction * (1 / |longest component|).  The
+// reference recomputes it at every region entry from the same direction, so it is a per-ray constant.
+VRM_HD RayDir scaled_raydir(const RayDir& k)
+{
+	float s = vdiv(1.0f, fabsf(k.d[0]));
+	return make_raydir(vmul(s, k.d[0]), vmul(s, k.d[1]), vmul(s, k.d[2]));
+}
+
 struct LaState
 {
 	float oo[3], od[3];  // oldRay origin / longest-axis-scaled direction
@@ -490,14 +574,12 @@ struct LaState
 
 // performVoxelSpaceJump (Renderer.cuh:696-751) / performShadowVoxelSpaceJump (Renderer.cuh:441-492)
 template <int ST, bool STATS, bool SHADOW>
-VRM_HD uint32_t voxel_space_jump(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, LaState& s, float* origO, const int* reg, HitInfo& h)
+VRM_HD uint32_t voxel_space_jump(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, LaState& s, const RayDir& ko, float* origO, const int* reg, HitInfo& h)
 {
 	float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, tMin = 0.0f;
 	while (!space_exists(c, r, p, s.g[0], s.g[1], s.g[2]))
 	{
-		t0 = vdiv(vsub((float)cluster_edge(s.od[0], s.g[0]), s.oo[0]), s.od[0]);
-		t1 = vdiv(vsub((float)cluster_edge(s.od[1], s.g[1]), s.oo[1]), s.od[1]);
-		t2 = vdiv(vsub((float)cluster_edge(s.od[2], s.g[2]), s.oo[2]), s.od[2]);
+		t_to3<false>(ko, (float)cluster_edge(s.od[0], s.g[0]), (float)cluster_edge(s.od[1], s.g[1]), (float)cluster_edge(s.od[2], s.g[2]), s.oo, t0, t1, t2);
 		tMin = vadd(min3(t0, t1, t2), kEps);
 		s.oo[0] = along(s.oo[0], tMin, s.od[0]); s.oo[1] = along(s.oo[1], tMin, s.od[1]); s.oo[2] = along(s.oo[2], tMin, s.od[2]);
 		s.g[0] = (int)floorf(s.oo[0]); s.g[1] = (int)floorf(s.oo[1]); s.g[2] = (int)floorf(s.oo[2]);
@@ -522,7 +604,7 @@ VRM_HD uint32_t voxel_space_jump(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, c
 		return col;
 	}
 	// re-snap to the longest axis, Renderer.cuh:742-747
-	float tNext = s.od[0] > 0.0f ? vdiv(vsub(ceilf(s.oo[0]), s.oo[0]), s.od[0]) : vdiv(vsub(floorf(s.oo[0]), s.oo[0]), s.od[0]);
+	float tNext = div1(vsub(s.od[0] > 0.0f ? ceilf(s.oo[0]) : floorf(s.oo[0]), s.oo[0]), ko, 0);
 	float tt = vadd(tNext, kEps);
 	s.ro[0] = along(s.oo[0], tt, s.od[0]); s.ro[1] = along(s.oo[1], tt, s.od[1]); s.ro[2] = along(s.oo[2], tt, s.od[2]);
 	s.ad[1] = (int)s.ro[1] - s.g[1];
@@ -538,11 +620,11 @@ VRM_HD uint32_t voxel_space_jump(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, c
 // slots to test (packed 2 bits each into `seq`); one shared test site then runs 1-3 times.  Same tests in the same
 // order, but lanes of a warp that are in different sub-cases execute the same instructions instead of serialising.
 template <int ST, bool STATS, bool SHADOW>
-VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, float* o, const float* d, const int* reg, HitInfo& h)
+VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, float* o, const RayDir& k, const RayDir& ko, const int* reg, HitInfo& h)
 {
+	const float* d = k.d;
 	LaState s;
-	float k = vdiv(1.0f, fabsf(d[0]));  // Ray.cuh:37,52,67
-	s.od[0] = vmul(k, d[0]); s.od[1] = vmul(k, d[1]); s.od[2] = vmul(k, d[2]);
+	s.od[0] = ko.d[0]; s.od[1] = ko.d[1]; s.od[2] = ko.d[2];  // scaled direction: constant along the ray, see scaled_raydir
 	s.oo[0] = o[0]; s.oo[1] = o[1]; s.oo[2] = o[2];
 	s.g[0] = (int)o[0]; s.g[1] = (int)o[1]; s.g[2] = (int)o[2];
 	s.ad[0] = d[0] < 0.0f ? -1 : 1;
@@ -562,7 +644,7 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 		if (s.ad[2] != 0 && s.ad[1] != 0)  // Renderer.cuh:792-805
 		{
 			float rounded = roundDown ? floorf(s.oo[1]) : ceilf(s.oo[1]);
-			float t1 = vdiv(vsub(rounded, s.oo[1]), s.od[1]);
+			float t1 = div1(vsub(rounded, s.oo[1]), ko, 1);
 			float shortestPosition = vadd(s.oo[2], vmul(s.od[2], t1));
 			int shorterDiff = (int)floorf(shortestPosition) - s.g[2];
 			seq = shorterDiff != 0 ? (2u | (1u << 2)) : (1u | (2u << 2));
@@ -581,7 +663,7 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 			s.g[2] += slot == 2 ? s.ad[2] : 0;
 			if (!space_exists(c, r, p, s.g[0], s.g[1], s.g[2]))
 			{
-				uint32_t j = voxel_space_jump<ST, STATS, SHADOW>(c, r, p, s, o, reg, h);
+				uint32_t j = voxel_space_jump<ST, STATS, SHADOW>(c, r, p, s, ko, o, reg, h);
 				if (j != kContinue) return j;
 				again = true;  // `continue` of the reference's while loop
 				break;
@@ -619,9 +701,9 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 	if (SHADOW)
 	{
 		float tt[4];
-		return march_steps<ST, STATS, PermRuntime, true>(c, r, p, o, d, reg, tt);
+		return march_steps<ST, STATS, PermRuntime, true>(c, r, p, o, k, reg, tt);
 	}
-	return march_original<ST, STATS, PermRuntime>(c, r, p, o, d, reg, h);
+	return march_original<ST, STATS, PermRuntime>(c, r, p, o, k, reg, h);
 }
 
 // isInShadowOriginalRayMarch (Renderer.cuh:174-235; LA = false, zero-direction guards) and
@@ -637,22 +719,26 @@ VRM_HD bool in_shadow(RayCtx<ST, STATS>& c, const float* originW, const int* reg
 	float o[3], d[3];
 	int reg[3];
 	to_walk(p, originW, o); to_walk(p, c.light.dir, d); to_walk(p, regW, reg);
+	// the light direction is the same for every shadow ray: these constants are loop-invariant for the whole kernel
+	const RayDir k = make_raydir(d[0], d[1], d[2]);
+	RayDir ko = k;
+	if constexpr (LA) ko = scaled_raydir(k);
 	int32_t ri = region_entry(c, p, reg);
 	while (ri != -2)
 	{
-		ri = skip_null_regions<ST, STATS, P, !LA>(c, p, o, d, reg, ri);
+		ri = skip_null_regions<ST, STATS, P, !LA>(c, p, o, k, reg, ri);
 		if (ri == -2) return false;
 		RegionRef<ST> r = load_region<ST>(c.sv, ri);
 		uint32_t col;
 		if constexpr (LA)
 		{
 			HitInfo unused;
-			col = march_longest_axis<ST, STATS, true>(c, r, p, o, d, reg, unused);
+			col = march_longest_axis<ST, STATS, true>(c, r, p, o, k, ko, reg, unused);
 		}
 		else
 		{
 			float t[4];
-			col = march_steps<ST, STATS, P, true>(c, r, p, o, d, reg, t);
+			col = march_steps<ST, STATS, P, true>(c, r, p, o, k, reg, t);
 		}
 		if (col != kEmpty) return true;
 		rebase_region(o, reg);
@@ -675,7 +761,7 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 	float sW[3] = {vmul(scale, vsub(originW[0], c.translation[0])), vmul(scale, vsub(originW[1], c.translation[1])), vmul(scale, vsub(originW[2], c.translation[2]))};
 	float o[3], d[3];
 	to_walk(p, sW, o); to_walk(p, dirW, d);
-	int reg[3] = {(int)floorf(vdiv(o[0], (float)kRegion)), (int)floorf(vdiv(o[1], (float)kRegion)), (int)floorf(vdiv(o[2], (float)kRegion))};
+	int reg[3] = {(int)floorf(vmul(o[0], 0.015625f)), (int)floorf(vmul(o[1], 0.015625f)), (int)floorf(vmul(o[2], 0.015625f))};
 	const int minC = c.sv.minCoord;
 	const uint32_t D = c.sv.diameter;
 	// scene-entry loop, Renderer.cuh:349-373
@@ -693,20 +779,23 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 		if (tMin == INFINITY) return 0;
 		float s = vadd(tMin, kEps);
 		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
-		reg[0] = (int)floorf(vdiv(o[0], (float)kRegion)); reg[1] = (int)floorf(vdiv(o[1], (float)kRegion)); reg[2] = (int)floorf(vdiv(o[2], (float)kRegion));
+		reg[0] = (int)floorf(vmul(o[0], 0.015625f)); reg[1] = (int)floorf(vmul(o[1], 0.015625f)); reg[2] = (int)floorf(vmul(o[2], 0.015625f));
 	}
 	// to region-local coordinates, Renderer.cuh:376-378
 	for (int i = 0; i < 3; i++) o[i] = vmul(1.0f, vsub(o[i], (float)(reg[i] * kRegion)));
+	const RayDir k = make_raydir(d[0], d[1], d[2]);
+	RayDir ko = k;
+	if constexpr (ALGO != kAlgoOriginal) ko = scaled_raydir(k);
 	int32_t ri = region_entry(c, p, reg);
 	while (ri != -2)
 	{
-		ri = skip_null_regions<ST, STATS, P, false>(c, p, o, d, reg, ri);
+		ri = skip_null_regions<ST, STATS, P, false>(c, p, o, k, reg, ri);
 		if (ri == -2) return 0;
 		RegionRef<ST> r = load_region<ST>(c.sv, ri);
 		HitInfo h;
 		uint32_t col;
-		if constexpr (ALGO == kAlgoOriginal) col = march_original<ST, STATS, P>(c, r, p, o, d, reg, h);
-		else col = march_longest_axis<ST, STATS, false>(c, r, p, o, d, reg, h);
+		if constexpr (ALGO == kAlgoOriginal) col = march_original<ST, STATS, P>(c, r, p, o, k, reg, h);
+		else col = march_longest_axis<ST, STATS, false>(c, r, p, o, k, ko, reg, h);
 		if (col != kEmpty)
 		{
 			// applyLighting(...) * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion)  (Renderer.cuh:314-315,821-822,...)

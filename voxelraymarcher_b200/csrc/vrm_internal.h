@@ -52,7 +52,7 @@ struct vrm_scene
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
 	int numSms = 148;
-	int renderMode = 0;               // 0 = flat state machine + persistent ray queue; 1 = nested form (VRM_RENDER_MODE=1, A/B only)
+	int renderMode = 1;               // 1 = nested loops, one CTA per 32x8 pixels (default: fastest so far); 0 = flat state machine + persistent ray queue (VRM_RENDER_MODE=0)
 
 	bool statsEnabled = false;
 	vrm::Stats* d_stats = nullptr;

@@ -229,7 +229,7 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 
 template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs& a, dim3 grid)
 {
-	if (s->renderMode == 1)  // nested form, one CTA per 32x8 pixels (kept for A/B measurements: VRM_RENDER_MODE=1)
+	if (s->renderMode == 1)  // nested form, one CTA per 32x8 pixels
 	{
 		if (s->statsEnabled) render_kernel<ST, ALGO, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		else render_kernel<ST, ALGO, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
