@@ -7,6 +7,14 @@ import pytest
 from tests.common import COMBOS, MINI_CAMERAS, PROBE_CAMERAS, build_oracle, camera, lookup_queries, oracle_kind, po, scenes
 
 
+@pytest.fixture(params=["nested", "flat"], autouse=True)
+def traversal_form(request):
+    """Both forms of the traversal the kernels are built from: vrm_core.cuh (nested loops) and vrm_flat.cuh (state machine)."""
+    po._lib("sim").sim_set_flat(1 if request.param == "flat" else 0)
+    yield request.param
+    po._lib("sim").sim_set_flat(1)
+
+
 @pytest.mark.parametrize("storage,algo", COMBOS)
 def test_core_matches_oracle_probe(storage, algo):
     kind = oracle_kind()
@@ -58,3 +66,32 @@ def test_core_lighting_variants(kw):
     finally:
         po.set_lighting(kind)
         po.set_lighting("sim")
+
+
+def axis_aligned_rays():
+    """Rays with exactly-zero direction components (+0 and -0), from inside and outside the scene: the unguarded divisions
+    of the reference produce inf / NaN here (SURVEY.md §7 hard part 3 'NaN/Inf behaviour')."""
+    dirs = []
+    for axis in range(3):
+        for sgn in (1.0, -1.0):
+            for z in (0.0, -0.0):
+                d = [z, z, z]
+                d[axis] = sgn
+                dirs.append(d)
+    dirs += [[0.6, 0.8, 0.0], [0.6, -0.8, -0.0], [0.0, 0.6, -0.8], [-0.0, -0.6, 0.8], [0.8, 0.0, 0.6], [-0.8, -0.0, -0.6]]
+    origins = [(40.3, 33.7, 36.2), (-30.5, 12.25, -70.75), (100.5, 40.5, 200.5), (32.0, 32.0, 32.0), (20.5, 300.5, -40.5)]
+    rays = [list(o) + d for o in origins for d in dirs]
+    return np.array(rays, np.float32)
+
+
+@pytest.mark.parametrize("storage,algo", COMBOS)
+def test_core_axis_aligned_rays_terminate_and_match(storage, algo):
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    po.set_lighting("sim")
+    xyz, rgb = scenes.probe_scene()
+    a, b = build_oracle(kind, xyz, rgb, storage), build_oracle("sim", xyz, rgb, storage)
+    rays = axis_aligned_rays()
+    ta, tb = a.trace_rays(rays, algo, threads=1), b.trace_rays(rays, algo, threads=1)
+    assert np.array_equal(ta["colour"], tb["colour"])
+    assert np.array_equal(ta["hits"], tb["hits"])

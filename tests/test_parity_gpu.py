@@ -239,3 +239,21 @@ def test_full_size_terrain_properties():
         differ = (hitsets[("vcs", algo)] != hitsets[("hashtable", algo)]).any(-1).mean()
         print(f"hashtable vs vcs hit maps differ on {differ:.2e} of the pixels ({algo})")
         assert differ < 0.05, differ
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("storage,algo", COMBOS)
+def test_axis_aligned_rays_terminate_and_match(probe, storage, algo):
+    """Exactly-zero direction components: inf / NaN in the reference's unguarded divisions.  The kernels must terminate
+    (the reference's own CUDA kernels would spin on a NaN position) and agree with the reference's HOST build."""
+    from tests.test_hostsim import axis_aligned_rays
+    xyz, rgb = probe
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    ref = build_oracle(kind, xyz, rgb, storage)
+    s = build_product(xyz, rgb, storage)
+    rays = axis_aligned_rays()
+    got = s.trace_rays(rays, algo, want_hits=True)
+    want = ref.trace_rays(rays, algo, threads=1)
+    assert np.array_equal(got["colour"], want["colour"])
+    assert np.array_equal(got["hits"], want["hits"])

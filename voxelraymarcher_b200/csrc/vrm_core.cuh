@@ -470,6 +470,11 @@ VRM_HD void rebase_region(float* o, int* reg)
 	}
 }
 
+// A NaN position (only reachable when a direction component is exactly +0 in the unguarded divisions: -inf * 0) makes
+// the reference's host build leave the scene -- (int)NaN is INT_MIN there -- whereas CUDA's saturating conversion gives 0
+// and the reference's own kernels (and a literal translation) would spin forever.  Follow the host build: NaN = outside.
+VRM_HD bool position_sane(const float* o) { return o[0] == o[0] && o[1] == o[1] && o[2] == o[2]; }
+
 // Null-region skip, Renderer.cuh:384-410 (GUARD: 185-211).  On return ri >= 0 (a stored region) or -2 (left the scene).
 template <int ST, bool STATS, class P, bool GUARD>
 VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, const RayDir& k, int* reg, int32_t ri)
@@ -485,7 +490,7 @@ VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, con
 		float tMin = min3(a0, a1, a2);
 		o[0] = along(o[0], tMin, d[0]); o[1] = along(o[1], tMin, d[1]); o[2] = along(o[2], tMin, d[2]);
 		rebase_region(o, reg);
-		ri = region_entry(c, p, reg);
+		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
 	}
 	return ri;
 }
@@ -742,7 +747,7 @@ VRM_HD bool in_shadow(RayCtx<ST, STATS>& c, const float* originW, const int* reg
 		}
 		if (col != kEmpty) return true;
 		rebase_region(o, reg);
-		ri = region_entry(c, p, reg);
+		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
 	}
 	return false;
 }
@@ -809,7 +814,7 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 			return lit * (uint32_t)!shadowed;
 		}
 		rebase_region(o, reg);
-		ri = region_entry(c, p, reg);
+		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
 	}
 	return 0;
 }

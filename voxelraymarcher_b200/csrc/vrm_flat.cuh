@@ -82,8 +82,7 @@ struct FlatRay
 	{
 		rebase_region(o, reg);
 		// float -> int of a NaN is INT_MIN on the reference's host build, i.e. "outside the scene"; CUDA would give 0 and spin
-		bool sane = o[0] == o[0] && o[1] == o[1] && o[2] == o[2];
-		ri = sane ? region_entry(c, p, reg) : -2;
+		ri = position_sane(o) ? region_entry(c, p, reg) : -2;  // see position_sane (vrm_core.cuh)
 		st = kStRegion;
 	}
 

@@ -1,0 +1,65 @@
+"""Multi-GPU sharding of multi-view batches (BASELINE.json configs[3]).
+
+Pixels and views are independent, so the path shards with NO data-path collective: the voxel structure is replicated
+(every rank builds it on its own GPU from the same voxel list -- the build is deterministic), each rank renders a
+contiguous block of the views in one launch (``vrm_render_views_device``), and the only exchange step is the gather of
+the finished RGB8 frames on rank 0 (NCCL over NVLink on the GPU box; gloo in the CPU tests, where the renderer is a stub).
+
+One process per GPU, ``torch.distributed`` for the plumbing.  The reference has no multi-GPU path at all
+(main/Main.cu:82-94 pins device 0).
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+
+def shard_views(n_views: int, world_size: int, rank: int) -> range:
+    """Contiguous block of view indices owned by ``rank``; the first ``n_views % world_size`` ranks get one more."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(n_views, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def gather_frames(local_frames, n_views: int, group=None, dst: int = 0):
+    """Gather per-rank frame blocks ``[n_local, H, W, 3]`` (uint8, same device on every rank) on ``dst``.
+    Returns the full ``[n_views, H, W, 3]`` tensor on ``dst`` and ``None`` elsewhere.  Ranks may own different numbers
+    of views, so blocks are padded to the largest block for the collective and trimmed afterwards."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = [len(shard_views(n_views, world, r)) for r in range(world)]
+    biggest = max(counts)
+    h, w = local_frames.shape[1:3]
+    block = local_frames
+    if block.shape[0] != biggest:
+        pad = torch.zeros((biggest - block.shape[0], h, w, 3), dtype=torch.uint8, device=local_frames.device)
+        block = torch.cat([block, pad], 0)
+    block = block.contiguous()
+    out = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+    dist.gather(block, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([o[:c] for o, c in zip(out, counts)], 0)
+
+
+def render_views_sharded(render_block: Callable[[Sequence, "object"], None], cameras: Sequence, width: int, height: int, device, group=None,
+                         dst: int = 0):
+    """Render ``cameras`` across the ranks of ``group`` and gather the frames on ``dst``.
+
+    ``render_block(cams, out)`` must fill ``out[i]`` (``[len(cams), H, W, 3]`` uint8 on ``device``) with the frame of
+    ``cams[i]`` -- on the GPU box it is ``lambda cams, out: scene.render_views_device(W, H, algo, cams, out.data_ptr())``.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = shard_views(len(cameras), world, rank)
+    local = torch.zeros((len(mine), height, width, 3), dtype=torch.uint8, device=device)
+    if len(mine):
+        render_block([cameras[i] for i in mine], local)
+    return gather_frames(local, len(cameras), group=group, dst=dst)
