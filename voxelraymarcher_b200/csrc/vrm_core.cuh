@@ -19,6 +19,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #include <type_traits>
 
 #if defined(__CUDACC__)
@@ -242,8 +243,7 @@ template <int ST> struct RegionRef;
 
 template <> struct RegionRef<kStorageHash>
 {
-	const unsigned long long* t1;
-	const unsigned long long* t2;
+	uint32_t base1, base2;  // first slot of table 1 / table 2 (32-bit indices into SceneView::slots: one IMAD.WIDE per probe)
 	uint32_t n, seed1, seed2;
 };
 
@@ -264,8 +264,8 @@ template <> VRM_HD RegionRef<kStorageHash> load_region<kStorageHash>(const Scene
 	HashRegionDesc d = sv.hashDesc[ri];
 #endif
 	RegionRef<kStorageHash> r;
-	r.t1 = sv.slots + d.slotBase;
-	r.t2 = r.t1 + d.n;
+	r.base1 = d.slotBase;
+	r.base2 = d.slotBase + d.n;
 	r.n = d.n; r.seed1 = d.seed1; r.seed2 = d.seed2;
 	return r;
 }
@@ -330,8 +330,8 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		const RegionRef<kStorageHash>& rh = r;
 		uint32_t key = ((uint32_t)g0 << (2 * p.cs(0))) | ((uint32_t)g1 << (2 * p.cs(1))) | ((uint32_t)g2 << (2 * p.cs(2)));
 		// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
-		unsigned long long e1 = ldg(rh.t1 + hash_slot1(key, rh.seed1, rh.n));
-		unsigned long long e2 = ldg(rh.t2 + hash_slot2(key, rh.seed2, rh.n));
+		unsigned long long e1 = ldg(c.sv.slots + (rh.base1 + hash_slot1(key, rh.seed1, rh.n)));
+		unsigned long long e2 = ldg(c.sv.slots + (rh.base2 + hash_slot2(key, rh.seed2, rh.n)));
 		if ((uint32_t)(e1 >> 32) == key) v = (uint32_t)e1;
 		else if ((uint32_t)(e2 >> 32) == key) v = (uint32_t)e2;
 		if (STATS) c.st.nProbe2++;
@@ -427,10 +427,30 @@ template <class P> VRM_HD int normal_axis_from_t(const P& p, float t0, float t1,
 
 // ---------------------------------------------------------------- shared walk helpers
 
-VRM_HD bool ray_in_region(const float* o)  // Renderer.cuh:93-98
+VRM_HD uint32_t float_bits(float f)
 {
-	return o[0] >= 0.0f && o[0] < (float)kRegion && o[1] >= 0.0f && o[1] < (float)kRegion && o[2] >= 0.0f && o[2] < (float)kRegion;
+#if defined(__CUDA_ARCH__)
+	return __float_as_uint(f);
+#else
+	uint32_t u;
+	memcpy(&u, &f, 4);
+	return u;
+#endif
 }
+// isRayInRegion, Renderer.cuh:93-98: 0 <= o_i < 64 on all axes.  Non-negative floats order like their bit patterns and
+// every negative float, NaN and +-inf has a pattern >= bits(64.0f), so three float range tests (seven instructions) are one
+// unsigned max and one compare.  The only value the two forms disagree on is -0.0f (in range for the reference), which a
+// position can never take: canonical_zero() removes it where a ray starts and sums / differences cannot produce it.
+VRM_HD bool ray_in_region(const float* o)
+{
+	uint32_t a = float_bits(o[0]), b = float_bits(o[1]), c = float_bits(o[2]);
+	uint32_t m = a > b ? a : b;
+	m = m > c ? m : c;
+	return m < 0x42800000u;
+}
+// -0.0f -> +0.0f, every other value unchanged.  Invisible to the reference's arithmetic (a zero's sign is never observed:
+// no division by a position, no copysign of one), see ray_in_region.
+VRM_HD float canonical_zero(float v) { return vadd(v, 0.0f); }
 VRM_HD bool grid_in_region(int x, int y, int z)  // Renderer.cuh:436-439
 {
 	return (uint32_t)x < (uint32_t)kRegion && (uint32_t)y < (uint32_t)kRegion && (uint32_t)z < (uint32_t)kRegion;
@@ -763,7 +783,8 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 	P p;
 	if constexpr (ALGO != kAlgoOriginal) p = rank_axes(dirW[0], dirW[1], dirW[2]);
 	// Ray::convertRayToLocalSpace, Ray.cuh:14-17
-	float sW[3] = {vmul(scale, vsub(originW[0], c.translation[0])), vmul(scale, vsub(originW[1], c.translation[1])), vmul(scale, vsub(originW[2], c.translation[2]))};
+	float sW[3] = {canonical_zero(vmul(scale, vsub(originW[0], c.translation[0]))), canonical_zero(vmul(scale, vsub(originW[1], c.translation[1]))),
+	               canonical_zero(vmul(scale, vsub(originW[2], c.translation[2])))};
 	float o[3], d[3];
 	to_walk(p, sW, o); to_walk(p, dirW, d);
 	int reg[3] = {(int)floorf(vmul(o[0], 0.015625f)), (int)floorf(vmul(o[1], 0.015625f)), (int)floorf(vmul(o[2], 0.015625f))};

@@ -91,7 +91,8 @@ struct FlatRay
 	{
 		shadow = false; shadowLA = false; lit = 0; result = 0;
 		if constexpr (ALGO != kAlgoOriginal) p = rank_axes(dirW[0], dirW[1], dirW[2]);
-		float sW[3] = {vmul(scale, vsub(originW[0], c.translation[0])), vmul(scale, vsub(originW[1], c.translation[1])), vmul(scale, vsub(originW[2], c.translation[2]))};
+		float sW[3] = {canonical_zero(vmul(scale, vsub(originW[0], c.translation[0]))), canonical_zero(vmul(scale, vsub(originW[1], c.translation[1]))),
+		               canonical_zero(vmul(scale, vsub(originW[2], c.translation[2])))};
 		float dw[3];
 		to_walk(p, sW, o); to_walk(p, dirW, dw);
 		k = make_raydir(dw[0], dw[1], dw[2]);
