@@ -19,7 +19,7 @@ constexpr int kTileW = 8, kTileH = 4;          // pixels per warp
 constexpr int kBlockTilesX = 4, kBlockTilesY = 2;
 constexpr int kBlockW = kTileW * kBlockTilesX;  // 32
 constexpr int kBlockH = kTileH * kBlockTilesY;  // 8
-constexpr int kRenderThreads = kBlockW * kBlockH;
+constexpr int kRenderThreads = kBlockW * kBlockH;  // resident CTAs per SM: 4 (<= 64 registers); 5 for hashtable + longest axis, which measured faster at 48 registers / 40 warps
 
 struct RenderArgs
 {
@@ -53,7 +53,7 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 }
 
 template <int ST, int ALGO, bool STATS>
-__global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t x = blockIdx.x * kBlockW + (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1));
