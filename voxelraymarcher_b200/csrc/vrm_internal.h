@@ -52,7 +52,7 @@ struct vrm_scene
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
 	int numSms = 148;
-	int renderMode = 1;               // 1 = nested loops, one CTA per 32x8 pixels (default: fastest so far); 0 = flat state machine + persistent ray queue (VRM_RENDER_MODE=0)
+	int renderMode = -1;              // -1 = per-combination default (vrm_render.cu); 0 = scheduled persistent kernel, 1 = nested loops, 2 = per-lane state machine (VRM_RENDER_MODE)
 
 	bool statsEnabled = false;
 	vrm::Stats* d_stats = nullptr;

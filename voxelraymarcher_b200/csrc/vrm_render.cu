@@ -52,7 +52,7 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 	}
 }
 
-template <int ST, int ALGO, bool STATS>
+template <int ST, int ALGO, bool STATS, bool FLATLOOP>
 __global__ void __launch_bounds__(kRenderThreads, (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(kRenderThreads, (ST == kStorageHash ? 5 : (ALG
 		for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
 		float o[3], d[3];
 		primary_ray(camv, x, y, a.W, a.H, o, d);
-		uint32_t color = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+		// FLATLOOP: the same tile mapping, but each lane runs the state machine of vrm_flat.cuh (one voxel test per iteration
+		// of a single loop) instead of the nested loops of vrm_core.cuh
+		uint32_t color = FLATLOOP ? march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale) : march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
 		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
 		// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
 		a.rgb[3 * p] = (uint8_t)(color >> 16);
@@ -83,16 +85,17 @@ __global__ void __launch_bounds__(kRenderThreads, (ST == kStorageHash ? 5 : (ALG
 	flush_stats<STATS>(c, a.stats);
 }
 
-// ---- persistent-thread ray queue -----------------------------------------------------------------------------------
+// ---- persistent-thread ray queue + warp-level state scheduling ------------------------------------------------------
 // Pixel slots are numbered tile-major: slot = (view * tilesPerView + tile) * 32 + pixel-in-8x4-tile, so that 32 consecutive
-// slots are one warp-coherent tile.  Every lane runs FlatRay micro-steps; when at least kRefillLanes lanes of a warp have
-// resolved their pixel (or all have), the idle lanes claim the next slots with ONE warp-aggregated atomicAdd and start new
-// primary rays, so divergent ray lengths no longer leave most of a warp idle until its slowest ray finishes.
+// slots are one warp-coherent tile.  Every lane owns one FlatRay state machine (vrm_flat.cuh).  Per iteration the warp
+// votes (__match_any_sync groups lanes by state, __reduce_min_sync picks the largest group) and runs ONLY that state's
+// code block; lanes in other states wait for their turn, lanes whose pixel is resolved vote for a refill, which claims the
+// next slots with one warp-aggregated atomicAdd.  Divergent ray lengths and phases therefore cost idle lanes only while a
+// state is in the minority, instead of serialising every loop nest as the nested kernels do.
 constexpr int kPersistThreads = 128;
-constexpr int kRefillLanes = 8;
 
 template <int ST, int ALGO, bool STATS>
-__global__ void __launch_bounds__(kPersistThreads) render_persistent_kernel(const RenderArgs a)
+__global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const RenderArgs a)
 {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned total = a.nViews * a.tilesPerView * 32u;
@@ -107,18 +110,25 @@ __global__ void __launch_bounds__(kPersistThreads) render_persistent_kernel(cons
 	bool exhausted = false;  // warp-uniform: the queue has run dry
 	for (;;)
 	{
-		const bool idle = ray.st == kStDone;
-		const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, idle);
-		if (idleMask == 0xFFFFFFFFu && exhausted) break;
-		if (!exhausted && (idleMask == 0xFFFFFFFFu || __popc(idleMask) >= kRefillLanes))
+		const int st = ray.st;
+		const bool votes = !(st == kStDone && exhausted);
+		const int ballotState = votes ? st : 7;
+		const unsigned peers = __match_any_sync(0xFFFFFFFFu, ballotState);
+		const int key = votes ? (((32 - __popc(peers)) << 3) | st) : ((32 << 3) | 7);
+		const int best = __reduce_min_sync(0xFFFFFFFFu, key);
+		const int run = best & 7;
+		if (run == 7) break;  // every lane is idle and the queue is dry
+		if (run == kStDone)
 		{
+			// refill: the idle lanes are the largest group
+			const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, st == kStDone);
 			const int want = __popc(idleMask);
 			const int leader = __ffs(idleMask) - 1;
 			unsigned base = 0;
 			if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned)want);
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
 			if (base + want >= total) exhausted = true;
-			if (idle)
+			if (st == kStDone)
 			{
 				const unsigned slot = base + __popc(idleMask & ((1u << lane) - 1u));
 				if (slot < total)
@@ -146,15 +156,23 @@ __global__ void __launch_bounds__(kPersistThreads) render_persistent_kernel(cons
 					}
 				}
 			}
+			continue;
 		}
-		if (ray.st != kStDone && ray.step(c))
+		if (st == run)
 		{
-			const uint32_t color = ray.result;
-			// writeColorToFramebuffer, Renderer.cuh:1024-1031
-			a.rgb[3 * pixel] = (uint8_t)(color >> 16);
-			a.rgb[3 * pixel + 1] = (uint8_t)((color >> 8) & 0xFF);
-			a.rgb[3 * pixel + 2] = (uint8_t)(color & 0xFF);
-			if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+			if (run == kStMain) ray.do_main(c);
+			else if (run == kStRegion) ray.do_region(c);
+			else if (run == kStHit) ray.do_hit(c);
+			else if constexpr (ALGO != kAlgoOriginal) ray.do_head();
+			if (ray.st == kStDone)
+			{
+				const uint32_t color = ray.result;
+				// writeColorToFramebuffer, Renderer.cuh:1024-1031
+				a.rgb[3 * pixel] = (uint8_t)(color >> 16);
+				a.rgb[3 * pixel + 1] = (uint8_t)((color >> 8) & 0xFF);
+				a.rgb[3 * pixel + 2] = (uint8_t)(color & 0xFF);
+				if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+			}
 		}
 	}
 	flush_stats<STATS>(c, a.stats);
@@ -229,10 +247,20 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 
 template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs& a, dim3 grid)
 {
-	if (s->renderMode == 1)  // nested form, one CTA per 32x8 pixels
+	// Which form of the traversal runs is a measured choice per combination (512^3 terrain, 4K, B200):
+	// the per-lane state machine wins where cluster jumps nest inside the longest-axis loop (VCS + longest axis: 2.06 ms
+	// vs 2.87 ms nested); the nested loops win or tie elsewhere.  VRM_RENDER_MODE=0|1|2 forces one form for A/B runs.
+	const int mode = s->renderMode >= 0 ? s->renderMode : ((ST == kStorageVcs && ALGO != kAlgoOriginal) ? 2 : 1);
+	if (mode == 1)  // nested form, one CTA per 32x8 pixels
 	{
-		if (s->statsEnabled) render_kernel<ST, ALGO, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-		else render_kernel<ST, ALGO, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		return;
+	}
+	if (mode == 2)  // state machine per lane, one CTA per 32x8 pixels, no ray queue
+	{
+		if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		return;
 	}
 	// persistent kernel: as many CTAs as fit on the device at once (a multiple of the SM count)
@@ -240,14 +268,14 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs&
 	int& bps = blocksPerSm[ST][ALGO][s->statsEnabled ? 1 : 0];
 	if (bps == 0)
 	{
-		if (s->statsEnabled) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_persistent_kernel<ST, ALGO, true>, kPersistThreads, 0);
-		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_persistent_kernel<ST, ALGO, false>, kPersistThreads, 0);
+		if (s->statsEnabled) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_scheduled_kernel<ST, ALGO, true>, kPersistThreads, 0);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_scheduled_kernel<ST, ALGO, false>, kPersistThreads, 0);
 		if (bps < 1) bps = 1;
 	}
 	const unsigned blocks = (unsigned)(s->numSms * bps);
 	cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned int), s->stream);
-	if (s->statsEnabled) render_persistent_kernel<ST, ALGO, true><<<blocks, kPersistThreads, 0, s->stream>>>(a);
-	else render_persistent_kernel<ST, ALGO, false><<<blocks, kPersistThreads, 0, s->stream>>>(a);
+	if (s->statsEnabled) render_scheduled_kernel<ST, ALGO, true><<<blocks, kPersistThreads, 0, s->stream>>>(a);
+	else render_scheduled_kernel<ST, ALGO, false><<<blocks, kPersistThreads, 0, s->stream>>>(a);
 }
 
 template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a, unsigned grid)
