@@ -53,7 +53,7 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 }
 
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
-__global__ void __launch_bounds__(kRenderThreads, (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) render_kernel(const RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOriginal) ? 4 : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t x = blockIdx.x * kBlockW + (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1));
