@@ -49,6 +49,9 @@ struct vrm_scene
 	float* h_cams = nullptr;     // pinned staging for cameras
 	void* d_io = nullptr;        size_t ioBytes = 0;   // rays / lookup queries and results
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t copyStream = nullptr;          // vrm_render: D2H of finished bands overlaps the rendering of the next band
+	static constexpr int kMaxBands = 8;
+	cudaEvent_t evBand[kMaxBands] = {};
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
 	int numSms = 148;
@@ -82,7 +85,7 @@ void vrm_free_structure(vrm_scene* s);
 
 // vrm_render.cu
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
-                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits);
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase = 0, uint32_t yEnd = 0xFFFFFFFFu);
 int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float* translation, uint32_t scale, int algorithm,
                      uint32_t* d_colour, int32_t* d_hits);
 int vrm_launch_lookup(vrm_scene* s, const int32_t* d_xyz, uint64_t n, uint32_t* d_out, uint8_t* d_exists);

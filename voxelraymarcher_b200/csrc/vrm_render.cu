@@ -29,6 +29,7 @@ struct RenderArgs
 	float scale;
 	const float* cams;  // nViews x 15
 	uint32_t W, H;
+	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
 	uint8_t* rgb;       // nViews x H x W x 3
 	int32_t* hits;      // nullable, nViews x H x W x 4
 	Stats* stats;       // nullable
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOrig
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t x = blockIdx.x * kBlockW + (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1));
-	const uint32_t y = blockIdx.y * kBlockH + (warp / kBlockTilesX) * kTileH + (lane / kTileW);
-	const bool inside = x < a.W && y < a.H;
+	const uint32_t y = a.yBase + blockIdx.y * kBlockH + (warp / kBlockTilesX) * kTileH + (lane / kTileW);
+	const bool inside = x < a.W && y < a.yEnd;
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
@@ -287,22 +288,24 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a
 }  // namespace
 
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
-                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits)
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase, uint32_t yEnd)
 {
+	if (yEnd > H) yEnd = H;
 	RenderArgs a;
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
+	a.yBase = yBase; a.yEnd = yEnd;
 	a.queue = s->d_queue;
 	a.tilesX = (W + kTileW - 1) / kTileW;
 	a.tilesPerView = a.tilesX * ((H + kTileH - 1) / kTileH);
 	a.nViews = nViews;
 	if ((uint64_t)a.tilesPerView * nViews * 32ull >= (1ull << 32)) { s->lastError = "too many pixels for one launch"; return VRM_ERR_INVALID; }
-	if (s->statsEnabled)
+	if (s->statsEnabled && yBase == 0)
 	{
 		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
 		s->statsRays = (uint64_t)W * H * nViews;
 	}
-	dim3 grid((W + kBlockW - 1) / kBlockW, (H + kBlockH - 1) / kBlockH, nViews);
+	dim3 grid((W + kBlockW - 1) / kBlockW, (yEnd - yBase + kBlockH - 1) / kBlockH, nViews);
 	const bool hash = s->storage == VRM_STORAGE_HASHTABLE, orig = algorithm == VRM_ALGO_ORIGINAL;
 	if (hash && orig) launch_render_t<kStorageHash, kAlgoOriginal>(s, a, grid);
 	else if (hash) launch_render_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
