@@ -257,3 +257,18 @@ def test_axis_aligned_rays_terminate_and_match(probe, storage, algo):
     want = ref.trace_rays(rays, algo, threads=1)
     assert np.array_equal(got["colour"], want["colour"])
     assert np.array_equal(got["hits"], want["hits"])
+
+
+def test_pinned_host_buffer_is_written_directly(probe):
+    """vrm_render into page-locked memory (zero-copy stores from the kernel) equals the pageable path (device framebuffer +
+    copy), for an aligned and for a ragged resolution, hits included."""
+    import torch
+    xyz, rgb = probe
+    s = build_product(xyz, rgb, "vcs")
+    for (w, h) in ((640, 360), (333, 187)):
+        cam = api.Camera((14.0, 9.0, 12.0), (4.0, 3.0, 2.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h))
+        want = s.render(w, h, "longestaxis", cam, scale=8, want_hits=True)
+        pinned = torch.zeros((h, w, 3), dtype=torch.uint8).pin_memory()
+        got = s.render(w, h, "longestaxis", cam, scale=8, rgb_out=pinned.numpy())
+        assert np.array_equal(pinned.numpy(), want["rgb"])
+        assert got["rgb"] is not None and want["hits"][..., 3].sum() > 0

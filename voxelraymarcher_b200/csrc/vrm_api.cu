@@ -130,8 +130,7 @@ int vrm_scene_create(int device, vrm_scene** out)
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_stats, sizeof(Stats));
 	if (e == cudaSuccess) e = cudaMemset(s->d_stats, 0, sizeof(Stats));
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_queue, sizeof(unsigned int));
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking);
-	for (int i = 0; i < vrm_scene::kMaxBands && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->evBand[i], cudaEventDisableTiming);
+
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->numSms, cudaDevAttrMultiProcessorCount, device);
 	if (const char* mode = getenv("VRM_RENDER_MODE")) s->renderMode = atoi(mode);
 	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }
@@ -153,8 +152,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);
 	if (s->ownStream) cudaStreamDestroy(s->ownStream);
-	if (s->copyStream) cudaStreamDestroy(s->copyStream);
-	for (int i = 0; i < vrm_scene::kMaxBands; i++) if (s->evBand[i]) cudaEventDestroy(s->evBand[i]);
+
 	cudaGetLastError();
 	delete s;
 	return VRM_OK;
@@ -270,32 +268,29 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 	if (!rgb_out) { s->lastError = "rgb_out is NULL"; return VRM_ERR_INVALID; }
 	VRM_CUDA(s, cudaSetDevice(s->device));
 	const size_t px = (size_t)width * height;
-	void* p = s->d_fb; rc = ensure(s, &p, &s->fbBytes, px * 3); s->d_fb = static_cast<uint8_t*>(p);
-	if (rc) return rc;
-	if (hits_out) { p = s->d_hits; rc = ensure(s, &p, &s->hitsBytes, px * 16); s->d_hits = static_cast<int32_t*>(p); if (rc) return rc; }
+	// Pinned (page-locked) caller buffers are mapped into the device's address space: the kernel then writes the frame
+	// straight into them over PCIe (coalesced 96-byte row segments, vrm_render.cu) and no device-to-host copy is needed.
+	// Pageable buffers go through the handle's device framebuffer and a copy.
+	auto device_alias = [](void* host) -> void* {
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+		cudaGetLastError();
+		return nullptr;
+	};
+	uint8_t* d_rgb = static_cast<uint8_t*>(device_alias(rgb_out));
+	int32_t* d_hits = hits_out ? static_cast<int32_t*>(device_alias(hits_out)) : nullptr;
+	const bool copyRgb = d_rgb == nullptr, copyHits = hits_out && d_hits == nullptr;
+	void* p;
+	if (copyRgb) { p = s->d_fb; rc = ensure(s, &p, &s->fbBytes, px * 3); s->d_fb = static_cast<uint8_t*>(p); if (rc) return rc; d_rgb = s->d_fb; }
+	if (copyHits) { p = s->d_hits; rc = ensure(s, &p, &s->hitsBytes, px * 16); s->d_hits = static_cast<int32_t*>(p); if (rc) return rc; d_hits = s->d_hits; }
 	rc = upload_cameras(s, camera, 1);
 	if (rc) return rc;
-	// The frame is rendered in horizontal bands (multiples of the 8-row CTA height); the device-to-host copy of a finished
-	// band runs on a second stream while the next band renders, so the call costs ~max(render, copy) instead of their sum.
-	// (The scheduled persistent kernel and statistics runs use one launch.)
-	int bands = (s->renderMode == 0 || s->statsEnabled || height < 256) ? 1 : vrm_scene::kMaxBands;
-	const uint32_t rowsPerBand = ((height + bands - 1) / bands + 7u) & ~7u;
 	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
-	for (int b = 0; b < bands; b++)
-	{
-		const uint32_t y0 = (uint32_t)b * rowsPerBand;
-		if (y0 >= height) { bands = b; break; }
-		const uint32_t y1 = y0 + rowsPerBand < height ? y0 + rowsPerBand : height;
-		rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, s->d_fb, hits_out ? s->d_hits : nullptr, y0, y1);
-		if (rc) return rc;
-		VRM_CUDA(s, cudaEventRecord(s->evBand[b], s->stream));
-		VRM_CUDA(s, cudaStreamWaitEvent(s->copyStream, s->evBand[b], 0));
-		const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
-		VRM_CUDA(s, cudaMemcpyAsync(rgb_out + off * 3, s->d_fb + off * 3, cnt * 3, cudaMemcpyDeviceToHost, s->copyStream));
-		if (hits_out) VRM_CUDA(s, cudaMemcpyAsync(hits_out + off * 4, s->d_hits + off * 4, cnt * 16, cudaMemcpyDeviceToHost, s->copyStream));
-	}
+	rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, d_rgb, d_hits);
+	if (rc) return rc;
 	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
-	VRM_CUDA(s, cudaStreamSynchronize(s->copyStream));
+	if (copyRgb) VRM_CUDA(s, cudaMemcpyAsync(rgb_out, s->d_fb, px * 3, cudaMemcpyDeviceToHost, s->stream));
+	if (copyHits) VRM_CUDA(s, cudaMemcpyAsync(hits_out, s->d_hits, px * 16, cudaMemcpyDeviceToHost, s->stream));
 	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
 	if (kernel_ms) VRM_CUDA(s, cudaEventElapsedTime(kernel_ms, s->ev0, s->ev1));
 	return VRM_OK;

@@ -49,9 +49,6 @@ struct vrm_scene
 	float* h_cams = nullptr;     // pinned staging for cameras
 	void* d_io = nullptr;        size_t ioBytes = 0;   // rays / lookup queries and results
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	cudaStream_t copyStream = nullptr;          // vrm_render: D2H of finished bands overlaps the rendering of the next band
-	static constexpr int kMaxBands = 8;
-	cudaEvent_t evBand[kMaxBands] = {};
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
 	int numSms = 148;

@@ -29,6 +29,7 @@ struct RenderArgs
 	float scale;
 	const float* cams;  // nViews x 15
 	uint32_t W, H;
+	uint32_t rowWordsOk;   // 1 when every 32-pixel row segment starts on a 4-byte boundary (W * 3 % 4 == 0 and an aligned base)
 	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
 	uint8_t* rgb;       // nViews x H x W x 3
 	int32_t* hits;      // nullable, nViews x H x W x 4
@@ -57,14 +58,20 @@ template <int ST, int ALGO, bool STATS, bool FLATLOOP>
 __global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOriginal) ? 4 : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t x = blockIdx.x * kBlockW + (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1));
-	const uint32_t y = a.yBase + blockIdx.y * kBlockH + (warp / kBlockTilesX) * kTileH + (lane / kTileW);
+	const uint32_t lx = (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1)), ly = (warp / kBlockTilesX) * kTileH + (lane / kTileW);
+	const uint32_t x0 = blockIdx.x * kBlockW, y0 = a.yBase + blockIdx.y * kBlockH;
+	const uint32_t x = x0 + lx, y = y0 + ly;
 	const bool inside = x < a.W && y < a.yEnd;
+	// The CTA's 32x8 pixels are staged in shared memory and written as 8 rows of 96 contiguous bytes (24 words per row,
+	// one STG.32 per thread) instead of three scattered byte stores per pixel (Renderer.cuh:1027-1030); this is also what makes
+	// writing the frame straight into pinned host memory (vrm_render) efficient.
+	__shared__ uint32_t staged[kBlockH][kBlockW * 3 / 4];
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
+	uint32_t color = 0;
 	if (inside)
 	{
 		const float* cam = a.cams + (size_t)blockIdx.z * 15;
@@ -75,13 +82,30 @@ __global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOrig
 		primary_ray(camv, x, y, a.W, a.H, o, d);
 		// FLATLOOP: the same tile mapping, but each lane runs the state machine of vrm_flat.cuh (one voxel test per iteration
 		// of a single loop) instead of the nested loops of vrm_core.cuh
-		uint32_t color = FLATLOOP ? march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale) : march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+		color = FLATLOOP ? march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale) : march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
 		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
-		// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
+		if (a.hits) reinterpret_cast<int4*>(a.hits)[p] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+	}
+	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
+	const bool wholeBlock = x0 + kBlockW <= a.W && y0 + kBlockH <= a.yEnd && a.rowWordsOk;
+	if (wholeBlock)
+	{
+		uint8_t* sb = reinterpret_cast<uint8_t*>(&staged[ly][0]) + lx * 3;
+		sb[0] = (uint8_t)(color >> 16); sb[1] = (uint8_t)((color >> 8) & 0xFF); sb[2] = (uint8_t)(color & 0xFF);
+		__syncthreads();
+		if (threadIdx.x < kBlockH * (kBlockW * 3 / 4))
+		{
+			const uint32_t row = threadIdx.x / (kBlockW * 3 / 4), w = threadIdx.x % (kBlockW * 3 / 4);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + (((size_t)blockIdx.z * a.H + y0 + row) * a.W + x0) * 3);
+			dst[w] = staged[row][w];
+		}
+	}
+	else if (inside)
+	{
+		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
 		a.rgb[3 * p] = (uint8_t)(color >> 16);
 		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
 		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
-		if (a.hits) reinterpret_cast<int4*>(a.hits)[p] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 	}
 	flush_stats<STATS>(c, a.stats);
 }
@@ -295,6 +319,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
 	a.yBase = yBase; a.yEnd = yEnd;
+	a.rowWordsOk = ((W * 3u) % 4u == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 3u) == 0 && (((size_t)W * H * 3) % 4 == 0 || nViews == 1)) ? 1u : 0u;
 	a.queue = s->d_queue;
 	a.tilesX = (W + kTileW - 1) / kTileW;
 	a.tilesPerView = a.tilesX * ((H + kTileH - 1) / kTileH);
