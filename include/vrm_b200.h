@@ -130,7 +130,8 @@ int vrm_lookup(vrm_scene* scene, const int32_t* xyz, uint64_t n, uint32_t* out, 
 
 /* Event counters of the LAST render / trace call made with statistics enabled (vrm_set_statistics(scene, 1)):
  * out[0] exist checks, [1] exist checks answering false, [2] lookups, [3] lookups that found a voxel,
- * [4] hash table-2 probes, [5] region-table reads, [6] rays, [7] reserved.  Used for the roofline's algorithmic bytes. */
+ * [4] hash table-2 probes, [5] region-table reads, [6] rays, [7] cluster-skip iterations that were fast-forwarded
+ * (they are included in [0] and [1]).  Used for the roofline's algorithmic bytes. */
 int vrm_set_statistics(vrm_scene* scene, int enabled);
 int vrm_get_statistics(vrm_scene* scene, uint64_t out[8]);
 

@@ -5,6 +5,7 @@
 //   g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -fopenmp
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -46,6 +47,7 @@ struct SimScene
 };
 
 Lighting gLight = {{0.57735026f, 0.57735026f, 0.57735026f}, {1, 1, 1}, {10, 10, -10}, 0, 1};
+unsigned long long gCrawlSkipped = 0;  // cluster-skip iterations fast-forwarded by crawl_skip (render calls only)
 int gFlat = 1;  // 1: the flat state machine of vrm_flat.cuh (what the render kernels run); 0: the nested form of vrm_core.cuh
 
 template <int ST, int ALGO>
@@ -66,6 +68,7 @@ void render_rows(const SimScene& s, const float* cam, const float* tr, float sca
 		c.sv = s.view(); c.light = gLight;
 		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
 		uint64_t local[5] = {0, 0, 0, 0, 0};
+		unsigned long long crawl = 0;
 		#pragma omp for schedule(dynamic, 1)
 		for (int64_t y = 0; y < (int64_t)H; y++)
 			for (uint32_t x = 0; x < W; x++)
@@ -80,11 +83,13 @@ void render_rows(const SimScene& s, const float* cam, const float* tr, float sca
 				if (lookups) lookups[p] = (uint32_t)c.st.nLookup;
 				local[0] += c.st.nExist; local[1] += c.st.nExistFalse; local[2] += c.st.nLookup; local[3] += c.st.nLookupHit;
 				if (c.st.nLookup > local[4]) local[4] = c.st.nLookup;
+				crawl += c.st.nCrawlSkipped;
 			}
 		#pragma omp critical
 		{
 			for (int i = 0; i < 4; i++) total[i] += local[i];
 			if (local[4] > total[4]) total[4] = local[4];
+			gCrawlSkipped += crawl;
 		}
 	}
 	if (counters) memcpy(counters, total, sizeof(total));
@@ -123,6 +128,7 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 extern "C" {
 
 void sim_set_flat(int flat) { gFlat = flat; }
+unsigned long long sim_crawl_skipped() { unsigned long long v = gCrawlSkipped; gCrawlSkipped = 0; return v; }
 void* sim_scene_create() { return new SimScene(); }
 void sim_scene_destroy(void* h) { delete static_cast<SimScene*>(h); }
 
@@ -309,3 +315,30 @@ int sim_lookup(void* h, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* 
 }
 
 }  // extern "C"
+
+// Debug aid: step one ray through the state machine and print a window of micro-steps.
+extern "C" int sim_debug_ray(void* h, const float* ray, int algorithm, long from, long count)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage != kStorageVcs) return 1;
+	RayCtx<kStorageVcs, true> c;
+	c.sv = s->view(); c.light = gLight; c.translation[0] = c.translation[1] = c.translation[2] = 0.0f; c.reset();
+	float tr1 = 1.0f;
+	auto run = [&](auto& rayState) {
+		rayState.start_primary(c, ray, ray + 3, tr1);
+		long n = 0;
+		while (rayState.st != kStDone && n < from + count)
+		{
+			if (n >= from)
+				printf("step %ld st %d mode %d shadow %d reg %d %d %d o %.9g %.9g %.9g  d %.9g %.9g %.9g exist %llu/%llu\n", n, rayState.st, rayState.mode, (int)rayState.shadow,
+				       rayState.reg[0], rayState.reg[1], rayState.reg[2], rayState.o[0], rayState.o[1], rayState.o[2], rayState.k.d[0], rayState.k.d[1], rayState.k.d[2],
+				       c.st.nExist, c.st.nExistFalse);
+			rayState.step(c);
+			n++;
+		}
+		return n;
+	};
+	if (algorithm == kAlgoOriginal) { FlatRay<kStorageVcs, kAlgoOriginal, true> r; run(r); }
+	else { FlatRay<kStorageVcs, kAlgoLongestAxis, true> r; run(r); }
+	return 0;
+}

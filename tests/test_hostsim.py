@@ -95,3 +95,35 @@ def test_core_axis_aligned_rays_terminate_and_match(storage, algo):
     ta, tb = a.trace_rays(rays, algo, threads=1), b.trace_rays(rays, algo, threads=1)
     assert np.array_equal(ta["colour"], tb["colour"])
     assert np.array_equal(ta["hits"], tb["hits"])
+
+
+def crawl_scene_and_rays(n=1500, seed=5):
+    """Rays that get stuck on a cluster face of an empty VCS cluster and advance by EPSILON per skip iteration in the
+    reference (a small negative direction component, |d| < ulp(position) / (2 EPSILON)): three floors on the coordinate
+    planes, rays skimming above them.  The oracle executes ~5e7 cluster-skip iterations for these 3000 rays; the product
+    fast-forwards them (crawl_skip, vrm_core.cuh) and must stay bit-identical, event counters included."""
+    xyz, rgb = scenes.checker_floor(0, 64, 0, 64, y=0)
+    xyz = np.concatenate([xyz, xyz[:, [1, 2, 0]], xyz[:, [2, 0, 1]]])
+    rgb = np.concatenate([rgb, rgb, rgb])
+    rng = np.random.default_rng(seed)
+    o = np.stack([rng.uniform(33, 63.9, n), rng.uniform(20, 60, n), rng.uniform(0.5, 8, n)], 1)
+    d = np.stack([-rng.uniform(0.004, 0.018, n), -rng.uniform(0.1, 0.4, n), rng.uniform(0.8, 1, n)], 1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1)
+    rolled = rays.copy()
+    rolled[:, 0:3] = np.roll(rays[:, 0:3], 1, axis=1)
+    rolled[:, 3:6] = np.roll(rays[:, 3:6], 1, axis=1)
+    return xyz.astype(np.int32), rgb, np.concatenate([rays, rolled]).astype(np.float32)
+
+
+@pytest.mark.parametrize("algo", ["original", "longestaxis"])
+def test_core_crawl_fast_forward_is_bit_exact(algo):
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    po.set_lighting("sim")
+    xyz, rgb, rays = crawl_scene_and_rays()
+    a, b = build_oracle(kind, xyz, rgb, "vcs"), build_oracle("sim", xyz, rgb, "vcs")
+    ta, tb = a.trace_rays(rays, algo, want_counters=True), b.trace_rays(rays, algo, want_counters=True)
+    assert int(ta["counters"][0]) > 10_000_000          # the reference really does crawl here
+    for k in ("colour", "hits", "counters"):
+        assert np.array_equal(ta[k], tb[k]), k

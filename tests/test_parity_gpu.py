@@ -272,3 +272,24 @@ def test_pinned_host_buffer_is_written_directly(probe):
         got = s.render(w, h, "longestaxis", cam, scale=8, rgb_out=pinned.numpy())
         assert np.array_equal(pinned.numpy(), want["rgb"])
         assert got["rgb"] is not None and want["hits"][..., 3].sum() > 0
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("algo", ["original", "longestaxis"])
+def test_crawl_fast_forward_is_bit_exact(algo):
+    """Rays stuck on a cluster face (the reference advances them by EPSILON per iteration, ~5e7 iterations here): the
+    kernels fast-forward the crawl and must return the same colours, hit voxels and event counters."""
+    from tests.test_hostsim import crawl_scene_and_rays
+    xyz, rgb, rays = crawl_scene_and_rays()
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    ref = build_oracle(kind, xyz, rgb, "vcs")
+    s = build_product(xyz, rgb, "vcs")
+    s.set_statistics(True)
+    got = s.trace_rays(rays, algo, want_hits=True)
+    st = s.get_statistics()
+    want = ref.trace_rays(rays, algo, want_counters=True)
+    assert np.array_equal(got["colour"], want["colour"])
+    assert np.array_equal(got["hits"], want["hits"])
+    assert [st["exist_checks"], st["exist_false"], st["lookups"], st["lookup_hits"]] == [int(v) for v in want["counters"][:4]]
+    assert st["crawl_skipped"] > 10_000_000

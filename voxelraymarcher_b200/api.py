@@ -279,5 +279,5 @@ class VoxelScene:
     def get_statistics(self):
         out = np.zeros(8, np.uint64)
         self._check(self.lib.vrm_get_statistics(self.h, _ptr(out)), "vrm_get_statistics")
-        keys = ["exist_checks", "exist_false", "lookups", "lookup_hits", "table2_probes", "region_reads", "rays", "reserved"]
+        keys = ["exist_checks", "exist_false", "lookups", "lookup_hits", "table2_probes", "region_reads", "rays", "crawl_skipped"]
         return {k: int(v) for k, v in zip(keys, out)}

@@ -373,7 +373,7 @@ int vrm_get_statistics(vrm_scene* s, uint64_t out[8])
 	VRM_CUDA(s, cudaMemcpyAsync(&h, s->d_stats, sizeof(Stats), cudaMemcpyDeviceToHost, s->stream));
 	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
 	out[0] = h.nExist; out[1] = h.nExistFalse; out[2] = h.nLookup; out[3] = h.nLookupHit; out[4] = h.nProbe2; out[5] = h.nRegionReads;
-	out[6] = s->statsRays; out[7] = 0;
+	out[6] = s->statsRays; out[7] = h.nCrawlSkipped;
 	return VRM_OK;
 }
 

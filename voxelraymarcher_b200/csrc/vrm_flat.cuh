@@ -259,7 +259,18 @@ struct FlatRay
 			float a0, a1, a2;
 			div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), e, a0, a1, a2);
 			if (gd) { a0 = (e0 != 0.0f) ? a0 : INFINITY; a1 = (e1 != 0.0f) ? a1 : INFINITY; a2 = (e2 != 0.0f) ? a2 : INFINITY; }
-			const float m = min3(a0, a1, a2);
+			float m = min3(a0, a1, a2);
+			if (m == 0.0f && mode != kAdvNext)
+			{
+				// the ray sits on a cluster face it cannot leave: fast-forward the EPSILON crawl (crawl_skip, vrm_core.cuh)
+				const int skipped = crawl_skip(o, e, jump ? g[0] : (int)o[0], jump ? g[1] : (int)o[1], jump ? g[2] : (int)o[2]);
+				if (skipped > 0)
+				{
+					if (STATS) { c.st.nExist += skipped; c.st.nExistFalse += skipped; c.st.nCrawlSkipped += skipped; }
+					div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), e, a0, a1, a2);  // same cell, same edges; guards are moot on the fast path
+					m = min3(a0, a1, a2);
+				}
+			}
 			const float s = vadd(m, kEps);
 			if (mode == kAdvNext) { t0 = a0; t1 = a1; t2 = a2; tMin = m; }
 			if (jump) { t0 = a0; t1 = a1; t2 = a2; tMin = s; }

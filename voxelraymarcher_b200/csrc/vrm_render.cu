@@ -43,9 +43,9 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 {
 	if constexpr (STATS)
 	{
-		unsigned long long v[6] = {c.st.nExist, c.st.nExistFalse, c.st.nLookup, c.st.nLookupHit, c.st.nProbe2, c.st.nRegionReads};
+		unsigned long long v[7] = {c.st.nExist, c.st.nExistFalse, c.st.nLookup, c.st.nLookupHit, c.st.nProbe2, c.st.nRegionReads, c.st.nCrawlSkipped};
 #pragma unroll
-		for (int k = 0; k < 6; k++)
+		for (int k = 0; k < 7; k++)
 		{
 			unsigned long long x = v[k];
 			for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
