@@ -80,7 +80,7 @@ void render_rows(const SimScene& s, const float* cam, const float* tr, float sca
 				size_t p = (size_t)y * W + x;
 				rgb[3 * p] = (uint8_t)(color >> 16); rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF); rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
 				if (hits) memcpy(hits + 4 * p, c.hit, 16);
-				if (lookups) lookups[p] = (uint32_t)c.st.nLookup;
+				if (lookups) lookups[p] = getenv("SIM_COUNT_STEPS") ? (uint32_t)(c.st.nExist - c.st.nCrawlSkipped) : (uint32_t)c.st.nLookup;
 				local[0] += c.st.nExist; local[1] += c.st.nExistFalse; local[2] += c.st.nLookup; local[3] += c.st.nLookupHit;
 				if (c.st.nLookup > local[4]) local[4] = c.st.nLookup;
 				crawl += c.st.nCrawlSkipped;

@@ -216,7 +216,7 @@ struct TraceArgs
 	Stats* stats;
 };
 
-template <int ST, int ALGO, bool STATS>
+template <int ST, int ALGO, bool STATS, bool FLATLOOP>
 __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 {
 	unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 	{
 		float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
 		float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
-		a.colour[i] = march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale);
+		a.colour[i] = FLATLOOP ? march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale) : march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
 		if (a.hits) reinterpret_cast<int4*>(a.hits)[i] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 	}
 	flush_stats<STATS>(c, a.stats);
@@ -305,8 +305,20 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs&
 
 template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a, unsigned grid)
 {
-	if (s->statsEnabled) trace_kernel<ST, ALGO, true><<<grid, 256, 0, s->stream>>>(a);
-	else trace_kernel<ST, ALGO, false><<<grid, 256, 0, s->stream>>>(a);
+	// Arbitrary (incoherent) rays: the per-lane state machine measured faster than the nested loops for every combination
+	// (1024^3 sparse shells, 8.3 M random rays: original 11.7 vs 21.1 ms, longest axis 28.4 vs 31.2 ms), so it is the
+	// default here; VRM_RENDER_MODE=1 forces the nested form.
+	const int mode = s->renderMode == 1 ? 1 : 2;
+	if (mode == 2)
+	{
+		if (s->statsEnabled) trace_kernel<ST, ALGO, true, true><<<grid, 256, 0, s->stream>>>(a);
+		else trace_kernel<ST, ALGO, false, true><<<grid, 256, 0, s->stream>>>(a);
+	}
+	else
+	{
+		if (s->statsEnabled) trace_kernel<ST, ALGO, true, false><<<grid, 256, 0, s->stream>>>(a);
+		else trace_kernel<ST, ALGO, false, false><<<grid, 256, 0, s->stream>>>(a);
+	}
 }
 
 }  // namespace
