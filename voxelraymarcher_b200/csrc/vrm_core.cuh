@@ -250,8 +250,7 @@ template <> struct RegionRef<kStorageHash>
 
 template <> struct RegionRef<kStorageVcs>
 {
-	const uint2* hdr;
-	const uint32_t* cmask;
+	uint32_t ri;  // dense region index: header / cluster-mask addresses are formed from it at each use (one register, not two pointers)
 };
 
 template <int ST> VRM_HD RegionRef<ST> load_region(const SceneView& sv, int32_t ri);
@@ -274,8 +273,7 @@ template <> VRM_HD RegionRef<kStorageHash> load_region<kStorageHash>(const Scene
 template <> VRM_HD RegionRef<kStorageVcs> load_region<kStorageVcs>(const SceneView& sv, int32_t ri)
 {
 	RegionRef<kStorageVcs> r;
-	r.hdr = sv.headers + (size_t)ri * (512 * 16);
-	r.cmask = sv.clusterMask + (size_t)ri * 16;
+	r.ri = (uint32_t)ri;
 	return r;
 }
 
@@ -314,7 +312,7 @@ VRM_HD bool space_exists(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& 
 	{
 		const RegionRef<kStorageVcs>& rv = r;
 		uint32_t cid = ((uint32_t)(g0 >> 3) << p.cs(0)) | ((uint32_t)(g1 >> 3) << p.cs(1)) | ((uint32_t)(g2 >> 3) << p.cs(2));
-		e = (ldg(rv.cmask + (cid >> 5)) >> (cid & 31)) & 1u;
+		e = (ldg(c.sv.clusterMask + ((size_t)rv.ri * 16 + (cid >> 5))) >> (cid & 31)) & 1u;
 	}
 	if (STATS) { c.st.nExist++; if (!e) c.st.nExistFalse++; }
 	return e;
@@ -342,7 +340,7 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		const RegionRef<kStorageVcs>& rv = r;
 		uint32_t cid = ((uint32_t)(g0 >> 3) << p.cs(0)) | ((uint32_t)(g1 >> 3) << p.cs(1)) | ((uint32_t)(g2 >> 3) << p.cs(2));
 		uint32_t code = ((uint32_t)(g0 & 7) << p.cs(0)) | ((uint32_t)(g1 & 7) << p.cs(1)) | ((uint32_t)(g2 & 7) << p.cs(2));
-		uint2 h = ldg(rv.hdr + cid * 16 + (code >> 5));
+		uint2 h = ldg(c.sv.headers + (((size_t)rv.ri * 512 + cid) * 16 + (code >> 5)));
 		uint32_t bit = code & 31;
 		if ((h.x >> bit) & 1u) v = ldg(c.sv.values + h.y + popc32(h.x & ((1u << bit) - 1u)));
 	}

@@ -72,13 +72,11 @@ struct FlatRay
 	uint32_t seq;
 	int nTests;
 	bool roundDown;
-	// pending hit (kStHit)
-	uint32_t hitCol;
-	float hitPos[3];
-	int hitInfo;  // bits 0-1 normal axis (world), bit 2 normal sign negative, bit 3 longest-axis shadow routine
-	// result
-	uint32_t lit;     // shaded colour waiting for its shadow ray
-	uint32_t result;  // final pixel colour once st == kStDone
+	// A pending hit (kStHit) re-uses registers that are dead between the hit and the start of the shadow ray: its position
+	// lives in ro[], its packed normal / shadow-routine bits in `mode` (bits 0-1 normal axis (world), bit 2 normal sign
+	// negative, bit 3 longest-axis shadow routine) and its voxel colour in `result`.
+	// `result` = voxel colour (kStHit) -> shaded colour waiting for its shadow ray -> final pixel colour (kStDone).
+	uint32_t result;
 
 	VRM_HD bool guardSkip() const { return shadow && !shadowLA; }  // zero-direction guards in the null-region skip (Renderer.cuh:191-193)
 	VRM_HD bool guardAdv() const { return shadow; }                // ... and in shadowRayMarchVoxelGrid (Renderer.cuh:113-115)
@@ -100,7 +98,7 @@ struct FlatRay
 	// rayMarchVoxelScene / rayMarchVoxelSceneLongestAxis up to the first region (Renderer.cuh:338-378, 917-954)
 	VRM_HD void start_primary(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
 	{
-		shadow = false; shadowLA = false; lit = 0; result = 0;
+		shadow = false; shadowLA = false; result = 0;
 		if constexpr (kLA) p = rank_axes(dirW[0], dirW[1], dirW[2]);
 		float sW[3] = {canonical_zero(vmul(scale, vsub(originW[0], c.translation[0]))), canonical_zero(vmul(scale, vsub(originW[1], c.translation[1]))),
 		               canonical_zero(vmul(scale, vsub(originW[2], c.translation[2])))};
@@ -136,22 +134,22 @@ struct FlatRay
 	VRM_HD void record_hit(uint32_t col, const float* pos, int nAxisW, float nSign, bool laKind)
 	{
 		if (shadow) { finish(0); return; }  // any voxel on the shadow ray: colour * !inShadow = 0
-		hitCol = col;
-		hitPos[0] = pos[0]; hitPos[1] = pos[1]; hitPos[2] = pos[2];
-		hitInfo = nAxisW | (nSign < 0.0f ? 4 : 0) | (laKind ? 8 : 0);
+		result = col;
+		ro[0] = pos[0]; ro[1] = pos[1]; ro[2] = pos[2];
+		mode = nAxisW | (nSign < 0.0f ? 4 : 0) | (laKind ? 8 : 0);
 		st = kStHit;
 	}
 
 	VRM_HD void do_hit(RayCtx<ST, STATS>& c)
 	{
-		const int nAxisW = hitInfo & 3;
-		const float nSign = (hitInfo & 4) ? -1.0f : 1.0f;
-		const bool laKind = (hitInfo & 8) != 0;
+		const int nAxisW = mode & 3;
+		const float nSign = (mode & 4) ? -1.0f : 1.0f;
+		const bool laKind = (mode & 8) != 0;
 		float hitW[3];
 		int regW[3];
-		to_world(p, hitPos, hitW); to_world(p, reg, regW);
-		lit = apply_lighting(c.light, c.translation, hitCol, nAxisW, nSign, hitW, regW);
-		if (!c.light.useShadows) { finish(lit); return; }
+		to_world(p, ro, hitW); to_world(p, reg, regW);
+		result = apply_lighting(c.light, c.translation, result, nAxisW, nSign, hitW, regW);
+		if (!c.light.useShadows) { finish(result); return; }
 		shadow = true;
 		shadowLA = laKind;
 		if constexpr (kLA)
@@ -170,7 +168,7 @@ struct FlatRay
 	// ---- kStRegion ---------------------------------------------------------------------------------------------
 	VRM_HD void do_region(RayCtx<ST, STATS>& c)
 	{
-		if (ri == -2) { finish(shadow ? lit : 0u); return; }  // left the scene: background / not shadowed
+		if (ri == -2) { finish(shadow ? result : 0u); return; }  // left the scene: background / not shadowed
 		if (ri == -1)
 		{
 			// null-region skip to the region edge, no +EPSILON (Renderer.cuh:384-410, guarded twin 185-211)
