@@ -188,6 +188,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout, so everything
+    # before the final print goes to stderr.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from voxelraymarcher_b200 import api, scenes
@@ -216,7 +222,26 @@ def main():
     scene.set_stream(stream.cuda_stream)
 
     frame = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev)
-    gathered = [torch.zeros_like(frame) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # Exchange step (N > 1): the finished frames are gathered on rank 0.  Preferred form: FUSED into the render kernel --
+    # every rank maps rank 0's gather buffer through CUDA IPC and its kernel stores the frame straight into its slot over
+    # NVLink / NVSwitch (coalesced 96-byte row segments); a 4-byte NCCL all-reduce per step tells rank 0 the slots are
+    # complete.  Fallback (no peer access): render locally, then an NCCL gather of the 24.9 MB frames.
+    peer, exchange = None, "none"
+    if world > 1:
+        from voxelraymarcher_b200 import multigpu
+        try:
+            peer = multigpu.PeerFrameBuffer(world, WIDTH, HEIGHT, local_rank)
+            exchange = "fused: render kernel stores into rank 0's buffer over NVLink peer memory (CUDA IPC) + 4-byte NCCL all-reduce per step"
+        except Exception as exc:  # noqa: BLE001
+            peer, exchange = None, f"nccl gather of frames (peer mapping failed: {exc})"
+        flags = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if int(flags.item()) == 0 and peer is not None:
+            peer.close()
+            peer, exchange = None, "nccl gather of frames (peer mapping failed on another rank)"
+    out_ptr = peer.ptr_for(rank) if peer is not None else frame.data_ptr()
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
+    gathered = [torch.zeros_like(frame) for _ in range(world)] if (world > 1 and rank == 0 and peer is None) else None
     flush = torch.zeros(512 << 20, dtype=torch.uint8, device=dev)
     total = args.warmup + args.steps
     cams = [orbit_camera(api, 0) for i in range(total)]   # configs[2] is a single view: every rank renders SURVEY.md §8d-3's camera
@@ -224,10 +249,13 @@ def main():
     def step(i, ev0, ev1, evk):
         flush.add_(1)                       # evict L2 (512 MiB > 126 MB), not timed
         ev0.record(stream)
-        scene.render_device(WIDTH, HEIGHT, ALGORITHM, cams[i], frame.data_ptr())
+        scene.render_device(WIDTH, HEIGHT, ALGORITHM, cams[i], out_ptr)
         evk.record(stream)
         if world > 1:
-            dist.gather(frame, gathered, dst=0)
+            if peer is not None:
+                dist.all_reduce(token)           # completion signal: after it, every rank's frame is in rank 0's buffer
+            else:
+                dist.gather(frame, gathered, dst=0)
         ev1.record(stream)
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(total)]
@@ -270,6 +298,15 @@ def main():
             e2e_s += dt
     clocks = sampler.stop() if rank == 0 else None
 
+    exchange_ok = None
+    if peer is not None:
+        # outside the timed region: the gathered slots must equal a local render of the same camera
+        scene.render_device(WIDTH, HEIGHT, ALGORITHM, cams[-1], frame.data_ptr())
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        if rank == 0:
+            full = peer.to_tensor()
+            exchange_ok = bool(all(torch.equal(full[r], frame) for r in range(world)))
     if world > 1:
         red = torch.tensor([t_ms, tk_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -302,7 +339,7 @@ def main():
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": WIDTH * HEIGHT * 3},
-            "gpu_launches": args.steps, "roofline": roofline,
+            "gpu_launches": args.steps, "roofline": roofline, "exchange": exchange, "exchange_verified": exchange_ok,
             "ms_per_frame_kernel": tk_ms / args.steps, "value_without_gather": value_no_gather, "wall_s_timed_region": wall,
             "build": {"ms": build_ms, "mvoxels_per_s": xyz.shape[0] / build_ms / 1e3, "voxels": int(xyz.shape[0]), "unique_voxels": info["unique_voxels"],
                       "regions": info["filled"], "structure_bytes": info["bytes"]},
@@ -313,7 +350,11 @@ def main():
     scene.close()
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
 

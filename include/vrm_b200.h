@@ -124,6 +124,20 @@ int vrm_trace_rays(vrm_scene* scene, const float* rays, uint64_t n, const float 
 int vrm_trace_rays_device(vrm_scene* scene, const float* d_rays, uint64_t n, const float translation[3],
                           uint32_t scale, int algorithm, uint32_t* d_colour_out, int32_t* d_hits_out);
 
+/* ---- multi-GPU exchange over NVLink peer memory ------------------------------------------------------------------
+ * The path's only exchange step is the gather of finished frames on one GPU.  Instead of rendering locally and then
+ * running a collective, a rank can hand vrm_render_device / vrm_render_views_device a pointer into the GATHERING GPU's
+ * memory: the render kernel then stores its frame (coalesced 96-byte row segments) straight through NVLink / NVSwitch
+ * while it computes.  These helpers create such a buffer on the gathering rank (cudaMalloc + CUDA IPC handle, 64 bytes,
+ * to be sent to the other processes by any means) and map it in the other processes.  One process per GPU.          */
+#define VRM_IPC_HANDLE_BYTES 64
+int vrm_peer_alloc(int device, uint64_t bytes, void** d_ptr_out, unsigned char handle_out[VRM_IPC_HANDLE_BYTES]);
+int vrm_peer_open(int device, const unsigned char handle[VRM_IPC_HANDLE_BYTES], void** d_ptr_out);
+int vrm_peer_close(int device, void* d_ptr);   /* for pointers from vrm_peer_open  */
+int vrm_peer_free(int device, void* d_ptr);    /* for pointers from vrm_peer_alloc */
+/* cudaMemcpy (device to device, synchronous) between raw device pointers, e.g. out of a peer buffer into a framework tensor. */
+int vrm_copy_device(int device, void* d_dst, const void* d_src, uint64_t bytes);
+
 /* The storage seam on GLOBAL voxel coordinates: out[i] = colour or VRM_EMPTY; exists_out[i] (nullable) =
  * doesVoxelSpaceExist (always 1 inside a non-empty region for the hash table; cluster occupancy for the VCS). */
 int vrm_lookup(vrm_scene* scene, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* exists_out);

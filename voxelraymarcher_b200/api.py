@@ -33,7 +33,7 @@ EXPORTS = [
     "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
-    "vrm_set_statistics", "vrm_get_statistics",
+    "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
 ]
 
 
@@ -78,6 +78,11 @@ def load_library():
         "vrm_trace_rays": (ci, [vp, vp, u64, vp, u32, ci, vp, vp, C.POINTER(f32)]),
         "vrm_trace_rays_device": (ci, [vp, vp, u64, vp, u32, ci, vp, vp]),
         "vrm_lookup": (ci, [vp, vp, u64, vp, vp]),
+        "vrm_peer_alloc": (ci, [ci, u64, C.POINTER(vp), vp]),
+        "vrm_peer_open": (ci, [ci, vp, C.POINTER(vp)]),
+        "vrm_peer_close": (ci, [ci, vp]),
+        "vrm_peer_free": (ci, [ci, vp]),
+        "vrm_copy_device": (ci, [ci, vp, vp, u64]),
         "vrm_set_statistics": (ci, [vp, ci]),
         "vrm_get_statistics": (ci, [vp, vp]),
     }

@@ -358,6 +358,55 @@ int vrm_lookup(vrm_scene* s, const int32_t* xyz, uint64_t n, uint32_t* out, uint
 	return VRM_OK;
 }
 
+int vrm_peer_alloc(int device, uint64_t bytes, void** d_ptr_out, unsigned char handle_out[VRM_IPC_HANDLE_BYTES])
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == VRM_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+	if (!d_ptr_out || !handle_out || bytes == 0) return VRM_ERR_INVALID;
+	*d_ptr_out = nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	void* p = nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_NOMEM; }
+	cudaIpcMemHandle_t h;
+	if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return VRM_ERR_CUDA; }
+	memcpy(handle_out, &h, VRM_IPC_HANDLE_BYTES);
+	*d_ptr_out = p;
+	return VRM_OK;
+}
+
+int vrm_peer_open(int device, const unsigned char handle[VRM_IPC_HANDLE_BYTES], void** d_ptr_out)
+{
+	if (!d_ptr_out || !handle) return VRM_ERR_INVALID;
+	*d_ptr_out = nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, VRM_IPC_HANDLE_BYTES);
+	void* p = nullptr;
+	if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	*d_ptr_out = p;
+	return VRM_OK;
+}
+
+int vrm_peer_close(int device, void* d_ptr)
+{
+	if (!d_ptr) return VRM_OK;
+	if (cudaSetDevice(device) != cudaSuccess || cudaIpcCloseMemHandle(d_ptr) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	return VRM_OK;
+}
+
+int vrm_peer_free(int device, void* d_ptr)
+{
+	if (!d_ptr) return VRM_OK;
+	if (cudaSetDevice(device) != cudaSuccess || cudaFree(d_ptr) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	return VRM_OK;
+}
+
+int vrm_copy_device(int device, void* d_dst, const void* d_src, uint64_t bytes)
+{
+	if (!d_dst || !d_src) return VRM_ERR_INVALID;
+	if (cudaSetDevice(device) != cudaSuccess || cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	return VRM_OK;
+}
+
 int vrm_set_statistics(vrm_scene* s, int enabled)
 {
 	if (!s) return VRM_ERR_INVALID;

@@ -63,3 +63,55 @@ def render_views_sharded(render_block: Callable[[Sequence, "object"], None], cam
     if len(mine):
         render_block([cameras[i] for i in mine], local)
     return gather_frames(local, len(cameras), group=group, dst=dst)
+
+
+class PeerFrameBuffer:
+    """The gathered frame buffer lives on rank ``dst`` and every other rank maps it through CUDA IPC, so that the render
+    kernels store their frames straight into it over NVLink / NVSwitch (``vrm_peer_*`` in include/vrm_b200.h): the exchange
+    is fused into the producing kernel instead of following it as a collective.  ``ptr_for(slot)`` is the device pointer a
+    rank passes to ``VoxelScene.render_device`` / ``render_views_device`` for global frame slot ``slot``."""
+
+    def __init__(self, n_frames: int, width: int, height: int, device: int, group=None, dst: int = 0):
+        import ctypes as C
+
+        import torch.distributed as dist
+        from . import api
+
+        self.lib = api.load_library()
+        self.device, self.dst = device, dst
+        self.rank = dist.get_rank(group)
+        self.frame_bytes = width * height * 3
+        self.shape = (n_frames, height, width, 3)
+        self.owner = self.rank == dst
+        self.ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if self.owner:
+            rc = self.lib.vrm_peer_alloc(device, n_frames * self.frame_bytes, C.byref(self.ptr), C.cast(handle, C.c_void_p))
+            if rc:
+                raise api.VrmError(f"vrm_peer_alloc failed: {rc}")
+        box = [bytes(handle) if self.owner else None]
+        dist.broadcast_object_list(box, src=dst, group=group)
+        if not self.owner:
+            raw = (C.c_ubyte * 64).from_buffer_copy(box[0])
+            rc = self.lib.vrm_peer_open(device, C.cast(raw, C.c_void_p), C.byref(self.ptr))
+            if rc:
+                raise api.VrmError(f"vrm_peer_open failed: {rc} (no peer access between the GPUs?)")
+
+    def ptr_for(self, slot: int) -> int:
+        return self.ptr.value + slot * self.frame_bytes
+
+    def to_tensor(self):
+        """Owner only: copy the gathered frames into a fresh torch tensor (after the producers have been synchronised)."""
+        import ctypes as C
+
+        import torch
+        out = torch.empty(self.shape, dtype=torch.uint8, device=f"cuda:{self.device}")
+        rc = self.lib.vrm_copy_device(self.device, C.c_void_p(out.data_ptr()), self.ptr, out.numel())
+        if rc:
+            raise RuntimeError(f"vrm_copy_device failed: {rc}")
+        return out
+
+    def close(self):
+        if self.ptr and self.ptr.value:
+            (self.lib.vrm_peer_free if self.owner else self.lib.vrm_peer_close)(self.device, self.ptr)
+            self.ptr.value = None
