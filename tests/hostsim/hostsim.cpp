@@ -65,7 +65,7 @@ void render_rows(const SimScene& s, const float* cam, const float* tr, float sca
 	#pragma omp parallel num_threads(nThreads)
 	{
 		RayCtx<ST, true> c;
-		c.sv = s.view(); c.light = gLight;
+		c.sv = s.view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = c.hit;
 		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
 		uint64_t local[5] = {0, 0, 0, 0, 0};
 		unsigned long long crawl = 0;
@@ -102,7 +102,7 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 	#pragma omp parallel num_threads(nThreads)
 	{
 		RayCtx<ST, true> c;
-		c.sv = s.view(); c.light = gLight;
+		c.sv = s.view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = c.hit;
 		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
 		uint64_t local[5] = {0, 0, 0, 0, 0};
 		#pragma omp for schedule(dynamic, 256)
@@ -322,7 +322,7 @@ extern "C" int sim_debug_ray(void* h, const float* ray, int algorithm, long from
 	SimScene* s = static_cast<SimScene*>(h);
 	if (s->storage != kStorageVcs) return 1;
 	RayCtx<kStorageVcs, true> c;
-	c.sv = s->view(); c.light = gLight; c.translation[0] = c.translation[1] = c.translation[2] = 0.0f; c.reset();
+	c.sv = s->view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = c.hit; c.translation[0] = c.translation[1] = c.translation[2] = 0.0f; c.reset();
 	float tr1 = 1.0f;
 	auto run = [&](auto& rayState) {
 		rayState.start_primary(c, ray, ray + 3, tr1);
@@ -330,8 +330,8 @@ extern "C" int sim_debug_ray(void* h, const float* ray, int algorithm, long from
 		while (rayState.st != kStDone && n < from + count)
 		{
 			if (n >= from)
-				printf("step %ld st %d mode %d shadow %d reg %d %d %d o %.9g %.9g %.9g  d %.9g %.9g %.9g exist %llu/%llu\n", n, rayState.st, rayState.mode, (int)rayState.shadow,
-				       rayState.reg[0], rayState.reg[1], rayState.reg[2], rayState.o[0], rayState.o[1], rayState.o[2], rayState.k.d[0], rayState.k.d[1], rayState.k.d[2],
+				printf("step %ld st %d mode %d shadow %d ureg %u %u %u o %.9g %.9g %.9g  d %.9g %.9g %.9g exist %llu/%llu\n", n, rayState.st, rayState.mode, (int)rayState.shadow(),
+				       rayState.ur[0], rayState.ur[1], rayState.ur[2], rayState.o[0], rayState.o[1], rayState.o[2], rayState.d[0], rayState.d[1], rayState.d[2],
 				       c.st.nExist, c.st.nExistFalse);
 			rayState.step(c);
 			n++;

@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvrm_b200.so")
+LIB_PATH = os.environ.get("VRM_B200_LIB") or os.path.join(HERE, "libvrm_b200.so")   # VRM_B200_LIB: an A/B build of the same library (tools/ab_variants.py)
 
 STORAGE_VCS, STORAGE_HASHTABLE = 0, 1          # StorageType {VOXEL_CLUSTER_STORE, HASH_TABLE}
 ALGO_LONGEST_AXIS, ALGO_ORIGINAL = 0, 1        # rayMarchFunctionID

@@ -133,6 +133,26 @@ VRM_HD void div3(float x0, float x1, float x2, const RayDir& k, float& a0, float
 	}
 }
 
+// the same with the constants passed one by one (vrm_flat.cuh keeps them in individual registers)
+VRM_HD void div3(float x0, float x1, float x2, float d0, float d1, float d2, float r0, float r1, float r2, float thr, float& a0, float& a1, float& a2)
+{
+	float m = fminf(fabsf(x0), fminf(fabsf(x1), fabsf(x2)));
+	if (!(m >= thr))
+	{
+		a0 = vdiv(x0, d0); a1 = vdiv(x1, d1); a2 = vdiv(x2, d2);
+	}
+	else
+	{
+		a0 = div_by_const(x0, d0, r0); a1 = div_by_const(x1, d1, r1); a2 = div_by_const(x2, d2, r2);
+	}
+}
+
+VRM_HD float div1(float x, float d, float rd, float thr)
+{
+	if (!(fabsf(x) >= thr)) return vdiv(x, d);
+	return div_by_const(x, d, rd);
+}
+
 VRM_HD float div1(float x, const RayDir& k, int i)
 {
 	float ax = fabsf(x);
@@ -149,6 +169,15 @@ struct Lighting
 	float pos[3];    // LIGHT_POSITION
 	int usePoint;    // USE_POINT_LIGHT
 	int useShadows;  // USE_SHADOWS
+};
+
+// The light direction prepared for the shadow rays of the state machine (vrm_flat.cuh make_light_walk; host-computed):
+// id* = world axis order (original-algorithm shadow routine), la* = ranked longest / middle / shortest order.
+struct LightWalk
+{
+	float idD[3], idR[3], idThr;
+	float laD[3], laR[3], laSD[3], laSR[3], laThr;
+	uint32_t laPerm;  // pack_perm() of the ranked order
 };
 
 struct HashRegionDesc  // 16 bytes, one LDG.128 per region entry
@@ -292,8 +321,15 @@ template <int ST, bool STATS> struct RayCtx
 {
 	SceneView sv;
 	Lighting light;
+	LightWalk lw;  // only the state machine of vrm_flat.cuh reads it
 	float translation[3];
-	int32_t hit[4];  // first voxel found by this ray (global x,y,z, flag) -- SURVEY.md F6
+	// First voxel found by this pixel's rays (global x,y,z, flag) -- SURVEY.md F6.  Every lookup site of the reference returns
+	// on the first stored voxel and the shadow ray only starts after the primary hit, so "the first non-empty lookup" IS the
+	// primary ray's hit.  Nested traversal (vrm_core.cuh): recorded by lookup_voxel in hit[].  State machine (vrm_flat.cuh):
+	// recorded at the hit site (record_hit_voxel) straight through hitOut (nullable; the kernels point it at the pixel's slot
+	// of the hit map, so no registers stay live for it; the host harness points it at hit[]).
+	int32_t* hitOut;
+	int32_t hit[4];
 	Stats st;
 
 	VRM_HD void reset()
@@ -320,6 +356,8 @@ VRM_HD bool space_exists(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& 
 
 // StorageStructure::lookupVoxel (CuckooHashTable.cuh:59-76; VoxelClusterStore.cuh:101-135): colour or kEmpty.
 // g0..g2 are region-local coordinates in walk order; reg[] the region in walk order (for the hit record).
+// The nested traversal records the pixel's first stored voxel here, in c.hit; the state machine of
+// vrm_flat.cuh has its own fused test site and records at the hit site instead.
 template <int ST, bool STATS, class P>
 VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, const int* reg, int g0, int g1, int g2)
 {
@@ -357,6 +395,17 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		}
 	}
 	return v;
+}
+
+// The hit map entry of a primary hit: region (walk order) * 64 + region-local voxel (walk order), stored in WORLD axes.
+template <int ST, bool STATS, class P>
+VRM_HD void record_hit_voxel(RayCtx<ST, STATS>& c, const P& p, const int* reg, int g0, int g1, int g2)
+{
+	if (!c.hitOut) return;
+	int gw[3] = {reg[0] * kRegion + g0, reg[1] * kRegion + g1, reg[2] * kRegion + g2};
+	int gx[3];
+	to_world(p, gw, gx);
+	c.hitOut[0] = gx[0]; c.hitOut[1] = gx[1]; c.hitOut[2] = gx[2]; c.hitOut[3] = 1;
 }
 
 // VoxelScene::isRayInScene + getRegionStorageStructure (renderer/Renderer.cuh:29-44): -2 = outside the table,
@@ -478,6 +527,13 @@ VRM_HD int cluster_edge(float d, int v)  // Renderer.cuh:293-295
 	return d > 0.0f ? ((v / 8) + 1) * 8 : (v / 8) * 8;
 }
 
+// cluster_edge for a voxel coordinate known to be non-negative (every call site inside a region: v in [0, 64)): the
+// truncating division is then a mask.  Same value as cluster_edge.
+VRM_HD int cluster_edge_u(float d, int v)
+{
+	return (int)(((uint32_t)v & ~7u) + (d > 0.0f ? 8u : 0u));
+}
+
 VRM_HD float bits_float(uint32_t u)
 {
 #if defined(__CUDA_ARCH__)
@@ -503,9 +559,9 @@ VRM_HD float bits_float(uint32_t u)
 // per axis: the result is bit-identical to executing them.  M is chosen so that all M skipped positions stay strictly
 // inside the cell and the binade; the step that leaves the cell is then executed normally.
 // Returns M (0 = nothing skipped).  v = voxel whose cluster is being skipped; the caller guarantees (int)o lies in that cell.
-VRM_HD int crawl_skip(float* o, const RayDir& k, int v0, int v1, int v2)
+VRM_HD int crawl_skip(float* o, const float* dir, float thr, int v0, int v1, int v2)
 {
-	if (!(k.thr == k.thr)) return 0;  // only rays on the exact-division fast path (no zero / tiny direction components)
+	if (!(thr == thr)) return 0;  // only rays on the exact-division fast path (no zero / tiny direction components)
 	const int v[3] = {v0, v1, v2};
 	int q[3];
 	int best = 0x7FFFFFFF;
@@ -516,7 +572,7 @@ VRM_HD int crawl_skip(float* o, const RayDir& k, int v0, int v1, int v2)
 		const float y = o[i];
 		const uint32_t yb = float_bits(y), eb = yb >> 23;
 		if (eb < 24u || eb > 140u) return 0;  // zero, denormal, tiny, negative (sign bit), inf / NaN
-		const float c = vmul(kEps, k.d[i]);
+		const float c = vmul(kEps, dir[i]);
 		const float cu = vmul(c, bits_float((277u - eb) << 23));  // c / ulp(y), exact power-of-two scaling
 		if (!(fabsf(cu) < 1048576.0f)) return 0;
 		if (vsub(cu, floorf(cu)) == 0.5f) return 0;  // exact tie: the additions alternate between two step sizes
@@ -533,7 +589,7 @@ VRM_HD int crawl_skip(float* o, const RayDir& k, int v0, int v1, int v2)
 		else
 		{
 			m = 0x7FFFFFFF;
-			if ((float)cluster_edge(k.d[i], v[i]) == y) stuck = true;  // this axis sits on its cluster face and cannot move: t_i = 0
+			if ((float)cluster_edge(dir[i], v[i]) == y) stuck = true;  // this axis sits on its cluster face and cannot move: t_i = 0
 		}
 		best = m < best ? m : best;
 		q[i] = qi;
@@ -543,6 +599,8 @@ VRM_HD int crawl_skip(float* o, const RayDir& k, int v0, int v1, int v2)
 	for (int i = 0; i < 3; i++) o[i] = bits_float(float_bits(o[i]) + (uint32_t)(best * q[i]));
 	return best;
 }
+
+VRM_HD int crawl_skip(float* o, const RayDir& k, int v0, int v1, int v2) { return crawl_skip(o, k.d, k.thr, v0, v1, v2); }
 
 // Renderer.cuh:421-429: move region coordinates by floor(o / 64) and rebase the local position
 VRM_HD void rebase_region(float* o, int* reg)
@@ -796,7 +854,7 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 						float tl = odS > 0.0f ? vdiv(vsub(ceilf(ooS), ooS), odS) : vdiv(vsub(floorf(ooS), ooS), odS);
 						h.pos[0] = along(s.oo[0], tl, s.od[0]); h.pos[1] = along(s.oo[1], tl, s.od[1]); h.pos[2] = along(s.oo[2], tl, s.od[2]);
 					}
-					h.laShadow = 1;
+							h.laShadow = 1;
 				}
 				return col;
 			}

@@ -1,19 +1,25 @@
 // vrm_flat.cuh -- the traversal of vrm_core.cuh re-expressed as a per-ray STATE MACHINE whose states are code blocks
-// that a warp can schedule.
+// that the lanes of a warp share.
 //
 // Why: the reference's control flow is four levels of nested data-dependent loops (scene walk > region march > voxel
 // steps / cluster jumps, then the same again for the shadow ray).  Executed as written, a warp serialises lanes that are
 // in different loops or have different trip counts: the first sm_100a capture showed 10.6 of 32 threads active per
 // instruction for VCS + longest axis (profiles/r01a_ncu_render_vcs_longestaxis.json).  Here a ray is always in one of five
 // states and each state's work is one block of straight-line code:
-//     kStRegion  enter the region under the ray (table entry already read): null-region skip / load the region / leave
+//     kStRegion  enter the region under the ray (table entry already read): leave / null region / load the region
 //     kStHead    longest axis only: loop condition of Renderer.cuh:787 + the order of this iteration's voxel tests
-//     kStMain    [one advance: next voxel edge | cluster edge | cluster jump] + ONE voxel test (space check + lookup)
+//     kStMain    [one advance: next voxel edge | cluster edge | cluster jump | null-region edge] + ONE voxel test
 //     kStHit     shade the hit (applyLighting) and turn the lane into the hit's shadow ray
-//     kStDone    pixel resolved (the lane can take a new pixel)
-// A warp then runs, per iteration, only the block that most of its lanes are waiting for (vrm_render.cu,
-// render_scheduled_kernel: __match_any_sync / __reduce_min_sync majority vote), so every executed instruction has many
-// active lanes whatever the individual rays' phases are.  `step()` runs the blocks in program order for single-ray callers.
+//     kStDone    pixel resolved
+// `step()` runs the blocks in program order (region -> head -> main), so a lane that enters a stored region does its
+// prologue, its loop head and its first voxel test in one pass, and ALL advances -- voxel steps, cluster skips, cluster
+// jumps and null-region skips, primary or shadow -- go through the one advance site and all voxel tests through the one
+// test site: lanes of a warp in different phases execute the same instructions.
+//
+// The per-ray state is kept small enough for 64 registers without spills (profiles/r01e: the previous layout spent 6 % of
+// its issue slots on local-memory traffic): the walk-space permutation is three storage shifts + three region-table
+// strides, flags are bits of one word, the tX/tY/tZ/tMin of the last advance are reduced to the three equality bits the
+// normal needs, and the light's direction constants come precomputed from the host (LightWalk).
 //
 // ARITHMETIC IS UNCHANGED: the same operations in the same order as vrm_core.cuh / the reference -- only the order in
 // which different rays' operations are interleaved changes.  tests/hostsim runs this very code on the CPU against the
@@ -34,52 +40,79 @@ enum FlatState : int
 	kStDone = 4
 };
 
-// What the advance of a kStMain step moves to.  All are "t_i = (next_i - o_i) / dir_i, o += (min t + EPSILON) * dir".
+// What the advance of a kStMain step moves to.  All are "t_i = (next_i - o_i) / dir_i, o += (min t [+ EPSILON]) * dir".
 enum AdvMode : int
 {
 	kAdvNone = 0,     // no advance: a longest-axis voxel test on gridValues
 	kAdvNext = 1,     // next voxel edge +-EPSILON                      (Renderer.cuh:269-280,320-331)
 	kAdvCluster = 2,  // cluster edge of the voxel under the ray        (Renderer.cuh:293-304)
-	kAdvJump = 3      // one iteration of performVoxelSpaceJump's loop   (Renderer.cuh:707-721): cluster edge of gridValues, scaled direction
+	kAdvJump = 3,     // one iteration of performVoxelSpaceJump's loop   (Renderer.cuh:707-721): cluster edge of gridValues, scaled direction
+	kAdvRegion = 4    // null-region skip to the region edge, no +EPSILON (Renderer.cuh:384-410, guarded twin 185-211)
 };
+
+// flag bits of FlatRay::fl
+constexpr uint32_t kFlShadow = 1u;       // this is the shadow ray of an already shaded hit
+constexpr uint32_t kFlShadowLA = 2u;     // ... walked with the longest-axis routines (Renderer.cuh:633-694) rather than the original ones (174-235)
+constexpr uint32_t kFlEq0 = 4u;          // t_i == tMin of the last kAdvNext / kAdvJump advance, walk slot i = bit 2 + i  (getNormalFromTValues)
+constexpr uint32_t kFlEqMask = 28u;
+constexpr int kFlPermShift = 8;          // bits 8-13: world axis of walk slot 0 / 1 / 2, two bits each
+
+VRM_HD PermRuntime unpack_perm(uint32_t fl)
+{
+	PermRuntime p;
+	p.a0 = (int)((fl >> kFlPermShift) & 3u); p.a1 = (int)((fl >> (kFlPermShift + 2)) & 3u); p.a2 = (int)((fl >> (kFlPermShift + 4)) & 3u);
+	return p;
+}
+VRM_HD uint32_t pack_perm(const PermRuntime& p) { return ((uint32_t)p.a0 | ((uint32_t)p.a1 << 2) | ((uint32_t)p.a2 << 4)) << kFlPermShift; }
+
+// The light's direction in the two walk spaces a shadow ray can use, with its exact-division constants: the same for every
+// shadow ray of a frame, so it is computed once on the host (same IEEE operations: make_raydir / scaled_raydir).
+VRM_HD LightWalk make_light_walk(const Lighting& L)
+{
+	LightWalk w;
+	const RayDir ki = make_raydir(L.dir[0], L.dir[1], L.dir[2]);
+	for (int i = 0; i < 3; i++) { w.idD[i] = ki.d[i]; w.idR[i] = ki.rd[i]; }
+	w.idThr = ki.thr;
+	const PermRuntime p = rank_axes(L.dir[0], L.dir[1], L.dir[2]);
+	float dw[3];
+	to_walk(p, L.dir, dw);
+	const RayDir k = make_raydir(dw[0], dw[1], dw[2]);
+	const RayDir ko = scaled_raydir(k);
+	for (int i = 0; i < 3; i++) { w.laD[i] = k.d[i]; w.laR[i] = k.rd[i]; w.laSD[i] = ko.d[i]; w.laSR[i] = ko.rd[i]; }
+	w.laThr = (k.thr == k.thr && ko.thr == ko.thr) ? k.thr : NAN;
+	w.laPerm = pack_perm(p);
+	return w;
+}
 
 template <int ST, int ALGO, bool STATS>
 struct FlatRay
 {
-	using P = typename std::conditional<ALGO == kAlgoOriginal, PermIdentity, PermRuntime>::type;
 	static constexpr bool kLA = ALGO != kAlgoOriginal;
 
 	// current ray (primary or shadow), region-local, walk space
-	float o[3];  // original algorithm: ray origin; longest axis: oldRay origin (the reference copies between the two only
-	             // at points where they are equal, Renderer.cuh:726,768,912)
-	RayDir k;    // direction + exact-division constants (vrm_core.cuh)
-	RayDir ko;   // the same for the longest-axis-scaled direction (Ray.cuh:69): per-ray constants, not per region
-	int reg[3];
-	int32_t ri;
-	RegionRef<ST> r;
-	P p;
+	float o[3];    // original algorithm: ray origin; longest axis: oldRay origin (the reference copies between the two only
+	               // at points where they are equal, Renderer.cuh:726,768,912)
+	float d[3], rd[3];    // direction and RN(1 / d): exact division by a per-ray constant (vrm_core.cuh)
+	float sd[3], srd[3];  // the same for the longest-axis-scaled direction (Ray.cuh:69): per-ray constants, not per region
+	float thr;            // fast-division threshold: 2^-100 when every component of d (and sd) qualifies, else NaN
+	uint32_t ur[3];       // region coordinates minus minCoord (walk space); in the table <=> all < diameter
+	int32_t ri;           // table entry of the region under the ray: dense region index, -1 null region, -2 outside the table
+	RegionRef<ST> r;      // hash table: the region's descriptor (the VCS addresses everything from ri)
+	uint32_t sh[3];       // walk slot -> shift of its coordinate inside a storage code (VCS: 6/3/0 per world x/y/z; hash key: 12/6/0)
+	uint32_t rs[3];       // walk slot -> stride of its coordinate in the region table (1, D, D*D per world x/y/z)
 	int st;
-	bool shadow;    // this is the shadow ray of an already shaded hit
-	bool shadowLA;  // ... walked with the longest-axis routines (Renderer.cuh:633-694) rather than the original ones (174-235)
-	int mode;       // AdvMode of the next kStMain step
-	// tX,tY,tZ,tMin of the last kAdvNext advance (the OUTER values of Renderer.cuh:273-277: a cluster skip leaves them
-	// stale) or of the last kAdvJump advance (Renderer.cuh:713-716, tMin including +EPSILON); a ray is in one of the two
-	// phases at a time and each phase sets them before it can hit, so one set of registers serves both
-	float t0, t1, t2, tMin;
-	// longest-axis state (slot 0 = longest axis)
-	float ro[3];
-	int g[3], ad[3];
-	uint32_t seq;
-	int nTests;
-	bool roundDown;
-	// A pending hit (kStHit) re-uses registers that are dead between the hit and the start of the shadow ray: its position
-	// lives in ro[], its packed normal / shadow-routine bits in `mode` (bits 0-1 normal axis (world), bit 2 normal sign
-	// negative, bit 3 longest-axis shadow routine) and its voxel colour in `result`.
+	int mode;             // AdvMode of the next kStMain step; a pending hit (kStHit) keeps its packed normal / shadow-routine bits here
+	uint32_t fl;          // kFl* bits
+	// longest-axis state (slot 0 = longest axis).  g is also "the voxel under the ray" of the other advances.
+	float ro[3];          // ray origin (rayMarchVoxelGridLongestAxis' `ray`); a pending hit keeps its position here
+	int g[3];
+	int ad1, ad2;         // axisDiff of the middle / shortest slot (slot 0's is the sign of d[0])
+	uint32_t seq;         // slots still to test this iteration, two bits each, first in the low bits; slot 0 is always the last
 	// `result` = voxel colour (kStHit) -> shaded colour waiting for its shadow ray -> final pixel colour (kStDone).
 	uint32_t result;
 
-	VRM_HD bool guardSkip() const { return shadow && !shadowLA; }  // zero-direction guards in the null-region skip (Renderer.cuh:191-193)
-	VRM_HD bool guardAdv() const { return shadow; }                // ... and in shadowRayMarchVoxelGrid (Renderer.cuh:113-115)
+	VRM_HD bool shadow() const { return (fl & kFlShadow) != 0; }
+	VRM_HD bool shadowOriginal() const { return (fl & (kFlShadow | kFlShadowLA)) == kFlShadow; }  // zero-direction guards in the null-region skip (Renderer.cuh:191-193)
 
 	VRM_HD void finish(uint32_t colour)
 	{
@@ -87,55 +120,106 @@ struct FlatRay
 		st = kStDone;
 	}
 
+	VRM_HD void set_perm(const SceneView& sv, const PermRuntime& p)
+	{
+		fl = (fl & ~(63u << kFlPermShift)) | pack_perm(p);
+		const uint32_t D = sv.diameter;
+		const int a[3] = {p.a0, p.a1, p.a2};
+		for (int i = 0; i < 3; i++)
+		{
+			sh[i] = (uint32_t)(6 - 3 * a[i]) * (ST == kStorageHash ? 2u : 1u);
+			rs[i] = a[i] == 0 ? 1u : (a[i] == 1 ? D : D * D);
+		}
+	}
+
+	// VoxelScene::isRayInScene + getRegionStorageStructure (Renderer.cuh:29-44)
+	VRM_HD void read_region_entry(RayCtx<ST, STATS>& c)
+	{
+		const uint32_t D = c.sv.diameter;
+		if (!(ur[0] < D && ur[1] < D && ur[2] < D)) { ri = -2; return; }
+		if (STATS) c.st.nRegionReads++;
+		ri = ldg(c.sv.regionTable + (ur[0] * rs[0] + ur[1] * rs[1] + ur[2] * rs[2]));
+	}
+
 	// rebase into the neighbouring region after the ray left the current one (Renderer.cuh:421-429) and read its entry
 	VRM_HD void change_region(RayCtx<ST, STATS>& c)
 	{
-		rebase_region(o, reg);
-		ri = position_sane(o) ? region_entry(c, p, reg) : -2;  // see position_sane (vrm_core.cuh)
+		for (int i = 0; i < 3; i++)
+		{
+			const int diff = (int)floorf(vmul(o[i], 0.015625f));  // o / 64 (exact scaling by a power of two)
+			ur[i] += (uint32_t)diff;
+			o[i] = vsub(o[i], (float)(diff * kRegion));  // convertRayToLocalSpace(.., scale 1), Ray.cuh:14-17: the product with 1.0f is the identity
+		}
 		st = kStRegion;
+		if (!position_sane(o)) { ri = -2; return; }  // see position_sane (vrm_core.cuh)
+		read_region_entry(c);
 	}
 
 	// rayMarchVoxelScene / rayMarchVoxelSceneLongestAxis up to the first region (Renderer.cuh:338-378, 917-954)
 	VRM_HD void start_primary(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
 	{
-		shadow = false; shadowLA = false; result = 0;
+		fl = 0; result = 0; mode = kAdvNext; ri = -2; seq = 0; ad1 = ad2 = 0;
+		g[0] = g[1] = g[2] = 0; ro[0] = ro[1] = ro[2] = 0.0f;
+		PermRuntime p;
+		p.a0 = 0; p.a1 = 1; p.a2 = 2;
 		if constexpr (kLA) p = rank_axes(dirW[0], dirW[1], dirW[2]);
+		set_perm(c.sv, p);
 		float sW[3] = {canonical_zero(vmul(scale, vsub(originW[0], c.translation[0]))), canonical_zero(vmul(scale, vsub(originW[1], c.translation[1]))),
 		               canonical_zero(vmul(scale, vsub(originW[2], c.translation[2])))};
 		float dw[3];
 		to_walk(p, sW, o); to_walk(p, dirW, dw);
-		k = make_raydir(dw[0], dw[1], dw[2]);
-		if constexpr (kLA) ko = scaled_raydir(k);
-		reg[0] = (int)floorf(vmul(o[0], 0.015625f)); reg[1] = (int)floorf(vmul(o[1], 0.015625f)); reg[2] = (int)floorf(vmul(o[2], 0.015625f));
+		const RayDir k = make_raydir(dw[0], dw[1], dw[2]);
+		for (int i = 0; i < 3; i++) { d[i] = k.d[i]; rd[i] = k.rd[i]; }
+		thr = k.thr;
+		if constexpr (kLA)
+		{
+			const RayDir ko = scaled_raydir(k);
+			for (int i = 0; i < 3; i++) { sd[i] = ko.d[i]; srd[i] = ko.rd[i]; }
+			if (!(ko.thr == ko.thr)) thr = NAN;
+		}
+		int reg[3] = {(int)floorf(vmul(o[0], 0.015625f)), (int)floorf(vmul(o[1], 0.015625f)), (int)floorf(vmul(o[2], 0.015625f))};
 		const int minC = c.sv.minCoord;
 		const uint32_t D = c.sv.diameter;
 		while (reg[0] - minC < 0 || reg[1] - minC < 0 || reg[2] - minC < 0 ||
 		       (uint32_t)(reg[0] - minC) > D - 1 || (uint32_t)(reg[1] - minC) > D - 1 || (uint32_t)(reg[2] - minC) > D - 1)
 		{
-			int far = (int)(D + (uint32_t)minC);
-			float a0 = vdiv(vsub((float)((k.d[0] < 0.0f ? far : minC) * kRegion), o[0]), k.d[0]);
-			float a1 = vdiv(vsub((float)((k.d[1] < 0.0f ? far : minC) * kRegion), o[1]), k.d[1]);
-			float a2 = vdiv(vsub((float)((k.d[2] < 0.0f ? far : minC) * kRegion), o[2]), k.d[2]);
+			// scene-entry loop, Renderer.cuh:349-373
+			const int far = (int)(D + (uint32_t)minC);
+			float a0, a1, a2;
+			div3(vsub((float)((d[0] < 0.0f ? far : minC) * kRegion), o[0]), vsub((float)((d[1] < 0.0f ? far : minC) * kRegion), o[1]),
+			     vsub((float)((d[2] < 0.0f ? far : minC) * kRegion), o[2]), d[0], d[1], d[2], rd[0], rd[1], rd[2], thr, a0, a1, a2);
 			if (a0 <= 0.0f) a0 = INFINITY;
 			if (a1 <= 0.0f) a1 = INFINITY;
 			if (a2 <= 0.0f) a2 = INFINITY;
-			float m = min3(a0, a1, a2);
+			const float m = min3(a0, a1, a2);
 			if (m == INFINITY || m != m) { finish(0); return; }  // (a NaN tMin only arises from 0/0: treated as a miss)
-			float s = vadd(m, kEps);
-			o[0] = along(o[0], s, k.d[0]); o[1] = along(o[1], s, k.d[1]); o[2] = along(o[2], s, k.d[2]);
+			const float s = vadd(m, kEps);
+			o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
 			reg[0] = (int)floorf(vmul(o[0], 0.015625f)); reg[1] = (int)floorf(vmul(o[1], 0.015625f)); reg[2] = (int)floorf(vmul(o[2], 0.015625f));
 		}
-		for (int i = 0; i < 3; i++) o[i] = vmul(1.0f, vsub(o[i], (float)(reg[i] * kRegion)));
-		ri = region_entry(c, p, reg);
+		for (int i = 0; i < 3; i++)
+		{
+			o[i] = vsub(o[i], (float)(reg[i] * kRegion));  // Renderer.cuh:376-378
+			ur[i] = (uint32_t)(reg[i] - minC);
+		}
 		st = kStRegion;
+		read_region_entry(c);
 	}
 
 	// ---- kStHit: applyLighting(...) * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion)  (Renderer.cuh:314-315,821-822,...)
-	VRM_HD void record_hit(uint32_t col, const float* pos, int nAxisW, float nSign, bool laKind)
+	// v0..v2: the voxel that was hit (region-local, walk space), for the hit map
+	VRM_HD void record_hit(RayCtx<ST, STATS>& c, uint32_t col, float p0, float p1, float p2, int nAxisW, float nSign, bool laKind, int v0, int v1, int v2)
 	{
-		if (shadow) { finish(0); return; }  // any voxel on the shadow ray: colour * !inShadow = 0
+		if (shadow()) { finish(0); return; }  // any voxel on the shadow ray: colour * !inShadow = 0
+		if (c.hitOut)
+		{
+			const PermRuntime p = unpack_perm(fl);
+			const int minC = c.sv.minCoord;
+			const int reg[3] = {(int)ur[0] + minC, (int)ur[1] + minC, (int)ur[2] + minC};
+			record_hit_voxel(c, p, reg, v0, v1, v2);
+		}
 		result = col;
-		ro[0] = pos[0]; ro[1] = pos[1]; ro[2] = pos[2];
+		ro[0] = p0; ro[1] = p1; ro[2] = p2;
 		mode = nAxisW | (nSign < 0.0f ? 4 : 0) | (laKind ? 8 : 0);
 		st = kStHit;
 	}
@@ -144,59 +228,61 @@ struct FlatRay
 	{
 		const int nAxisW = mode & 3;
 		const float nSign = (mode & 4) ? -1.0f : 1.0f;
-		const bool laKind = (mode & 8) != 0;
+		const bool laKind = kLA && (mode & 8) != 0;
 		float hitW[3];
 		int regW[3];
-		to_world(p, ro, hitW); to_world(p, reg, regW);
+		{
+			const PermRuntime p = unpack_perm(fl);
+			const int minC = c.sv.minCoord;
+			const int reg[3] = {(int)ur[0] + minC, (int)ur[1] + minC, (int)ur[2] + minC};
+			to_world(p, ro, hitW); to_world(p, reg, regW);
+		}
 		result = apply_lighting(c.light, c.translation, result, nAxisW, nSign, hitW, regW);
 		if (!c.light.useShadows) { finish(result); return; }
-		shadow = true;
-		shadowLA = laKind;
-		if constexpr (kLA)
+		fl = kFlShadow | (laKind ? kFlShadowLA : 0u);
+		PermRuntime p;
+		p.a0 = 0; p.a1 = 1; p.a2 = 2;
+		if (laKind) p = unpack_perm(c.lw.laPerm);
+		set_perm(c.sv, p);
+		to_walk(p, hitW, o);
 		{
-			if (laKind) p = rank_axes(c.light.dir[0], c.light.dir[1], c.light.dir[2]);
-			else { p.a0 = 0; p.a1 = 1; p.a2 = 2; }
+			int regWalk[3];
+			to_walk(p, regW, regWalk);
+			const int minC = c.sv.minCoord;
+			for (int i = 0; i < 3; i++) ur[i] = (uint32_t)(regWalk[i] - minC);
 		}
-		float dw[3];
-		to_walk(p, hitW, o); to_walk(p, c.light.dir, dw); to_walk(p, regW, reg);
-		k = make_raydir(dw[0], dw[1], dw[2]);
-		if constexpr (kLA) { if (laKind) ko = scaled_raydir(k); }
-		ri = region_entry(c, p, reg);
+		if (laKind)
+		{
+			for (int i = 0; i < 3; i++) { d[i] = c.lw.laD[i]; rd[i] = c.lw.laR[i]; }
+			if constexpr (kLA) { for (int i = 0; i < 3; i++) { sd[i] = c.lw.laSD[i]; srd[i] = c.lw.laSR[i]; } }
+			thr = c.lw.laThr;
+		}
+		else
+		{
+			for (int i = 0; i < 3; i++) { d[i] = c.lw.idD[i]; rd[i] = c.lw.idR[i]; }
+			thr = c.lw.idThr;
+		}
 		st = kStRegion;
+		read_region_entry(c);
 	}
 
 	// ---- kStRegion ---------------------------------------------------------------------------------------------
 	VRM_HD void do_region(RayCtx<ST, STATS>& c)
 	{
-		if (ri == -2) { finish(shadow ? result : 0u); return; }  // left the scene: background / not shadowed
-		if (ri == -1)
-		{
-			// null-region skip to the region edge, no +EPSILON (Renderer.cuh:384-410, guarded twin 185-211)
-			float n0 = k.d[0] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
-			float n1 = k.d[1] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
-			float n2 = k.d[2] > 0.0f ? vadd((float)kRegion, kEps) : vsub(0.0f, kEps);
-			float a0, a1, a2;
-			div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), k, a0, a1, a2);
-			if (guardSkip()) { a0 = (k.d[0] != 0.0f) ? a0 : INFINITY; a1 = (k.d[1] != 0.0f) ? a1 : INFINITY; a2 = (k.d[2] != 0.0f) ? a2 : INFINITY; }
-			const float m = min3(a0, a1, a2);
-			o[0] = along(o[0], m, k.d[0]); o[1] = along(o[1], m, k.d[1]); o[2] = along(o[2], m, k.d[2]);
-			change_region(c);
-			return;
-		}
+		if (ri == -2) { finish(shadow() ? result : 0u); return; }  // left the scene: background / not shadowed
+		if (ri == -1) { mode = kAdvRegion; st = kStMain; return; }  // null region: skip to its edge through the advance site
 		r = load_region<ST>(c.sv, ri);
 		bool la = false;
-		if constexpr (kLA) la = !(shadow && !shadowLA);
+		if constexpr (kLA) la = !shadowOriginal();
 		if (la)
 		{
-			// rayMarchVoxelGridLongestAxis prologue, Renderer.cuh:763-784
+			// rayMarchVoxelGridLongestAxis prologue, Renderer.cuh:763-784.  The reference divides by the scaled longest
+			// component +-1.0f: x / 1 = x and x / -1 = -x exactly.
 			g[0] = (int)o[0]; g[1] = (int)o[1]; g[2] = (int)o[2];
-			ad[0] = k.d[0] < 0.0f ? -1 : 1;
-			float t = ad[0] > 0 ? vdiv(vsub(vadd(vadd((float)g[0], kEps), 1.0f), o[0]), 1.0f)
-			                    : vdiv(vsub(vsub((float)g[0], kEps), o[0]), -1.0f);
-			ro[0] = along(o[0], t, ko.d[0]); ro[1] = along(o[1], t, ko.d[1]); ro[2] = along(o[2], t, ko.d[2]);
-			ad[1] = (int)ro[1] - g[1];
-			ad[2] = (int)ro[2] - g[2];
-			roundDown = ko.d[1] < 0.0f;
+			const float t = d[0] < 0.0f ? -vsub(vsub((float)g[0], kEps), o[0]) : vsub(vadd(vadd((float)g[0], kEps), 1.0f), o[0]);
+			ro[0] = along(o[0], t, sd[0]); ro[1] = along(o[1], t, sd[1]); ro[2] = along(o[2], t, sd[2]);
+			ad1 = (int)ro[1] - g[1];
+			ad2 = (int)ro[2] - g[2];
 			st = kStHead;
 		}
 		else { mode = kAdvNext; st = kStMain; }  // the region march starts with one step before the first test (Renderer.cuh:269-280)
@@ -205,43 +291,74 @@ struct FlatRay
 	// ---- kStHead (longest axis): Renderer.cuh:787-805 ------------------------------------------------------------------
 	VRM_HD void do_head()
 	{
-		if (!grid_in_region(g[0] + ad[0], g[1] + ad[1], g[2] + ad[2]))
+		const int ad0 = d[0] < 0.0f ? -1 : 1;
+		if (!grid_in_region(g[0] + ad0, g[1] + ad1, g[2] + ad2))
 		{
 			// Renderer.cuh:911-914: finish the region with the original algorithm from oldRay's origin (o already is it)
 			mode = kAdvNext;
 			st = kStMain;
 			return;
 		}
-		if (ad[2] != 0 && ad[1] != 0)
+		if (ad2 != 0 && ad1 != 0)
 		{
-			float rounded = roundDown ? floorf(o[1]) : ceilf(o[1]);
-			float tt = div1(vsub(rounded, o[1]), ko, 1);
-			float shortestPosition = vadd(o[2], vmul(ko.d[2], tt));
-			int shorterDiff = (int)floorf(shortestPosition) - g[2];
+			const float rounded = sd[1] < 0.0f ? floorf(o[1]) : ceilf(o[1]);  // Renderer.cuh:784
+			const float tt = div1(vsub(rounded, o[1]), sd[1], srd[1], thr);
+			const float shortestPosition = vadd(o[2], vmul(sd[2], tt));
+			const int shorterDiff = (int)floorf(shortestPosition) - g[2];
 			seq = shorterDiff != 0 ? (2u | (1u << 2)) : (1u | (2u << 2));
-			nTests = 3;
 		}
-		else if (ad[1] != 0) { seq = 1u; nTests = 2; }
-		else if (ad[2] != 0) { seq = 2u; nTests = 2; }
-		else { seq = 0u; nTests = 1; }
+		else if (ad1 != 0) seq = 1u;
+		else if (ad2 != 0) seq = 2u;
+		else seq = 0u;
 		mode = kAdvNone;
 		st = kStMain;
+	}
+
+	// ---- the voxel test: doesVoxelSpaceExist + lookupVoxel on region-local walk-space coordinates ---------------------------
+	// Returns whether the voxel space exists; col = colour or kEmpty.
+	VRM_HD bool voxel_test(RayCtx<ST, STATS>& c, int c0, int c1, int c2, uint32_t& col)
+	{
+		col = kEmpty;
+		if constexpr (ST == kStorageHash)
+		{
+			const uint32_t key = ((uint32_t)c0 << sh[0]) | ((uint32_t)c1 << sh[1]) | ((uint32_t)c2 << sh[2]);
+			// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
+			const unsigned long long e1 = ldg(c.sv.slots + (r.base1 + hash_slot1(key, r.seed1, r.n)));
+			const unsigned long long e2 = ldg(c.sv.slots + (r.base2 + hash_slot2(key, r.seed2, r.n)));
+			if ((uint32_t)(e1 >> 32) == key) col = (uint32_t)e1;
+			else if ((uint32_t)(e2 >> 32) == key) col = (uint32_t)e2;
+			if (STATS) { c.st.nExist++; c.st.nLookup++; c.st.nProbe2++; if (col != kEmpty) c.st.nLookupHit++; }
+			return true;
+		}
+		else
+		{
+			// One value carries both codes: cc = cluster id << 9 | in-cluster code.  A coordinate v in [0, 64) contributes
+			// (v & 7) | (v >> 3) << 9 = (v * 65) & 0xE07, shifted to its axis' place.
+			const uint32_t cc = ((((uint32_t)c0 * 65u) & 0xE07u) << sh[0]) | ((((uint32_t)c1 * 65u) & 0xE07u) << sh[1]) | ((((uint32_t)c2 * 65u) & 0xE07u) << sh[2]);
+			const uint32_t cid = cc >> 9;
+			const bool e = (ldg(c.sv.clusterMask + ((uint32_t)ri * 16u + (cid >> 5))) >> (cid & 31u)) & 1u;
+			if (STATS) { c.st.nExist++; if (!e) c.st.nExistFalse++; }
+			if (!e) return false;
+			// header word index inside the region = cid * 16 + code / 32 = cc >> 5; bit = code % 32 = cc % 32
+			const uint2 h = ldg(c.sv.headers + ((uint32_t)ri * 8192u + (cc >> 5)));
+			const uint32_t bit = cc & 31u;
+			if ((h.x >> bit) & 1u) col = ldg(c.sv.values + (h.y + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
+			if (STATS) { c.st.nLookup++; if (col != kEmpty) c.st.nLookupHit++; }
+			return true;
+		}
 	}
 
 	// ---- kStMain: [one advance] + one voxel test ------------------------------------------------------------------------
 	VRM_HD void do_main(RayCtx<ST, STATS>& c)
 	{
-		int c0, c1, c2, slot = 0;
+		int slot = 0;
 		const bool test = kLA && mode == kAdvNone;
 		const bool jump = kLA && mode == kAdvJump;
 		if (!test)
 		{
-			// zero-direction guards exist only in the shadow routines of the ORIGINAL algorithm (Renderer.cuh:113-115,137-139,
-			// 160-162); the longest-axis jump guards nothing (Renderer.cuh:457-459)
-			const bool gd = jump ? false : guardAdv();
-			RayDir e = k;
-			if constexpr (kLA) { if (jump) e = ko; }
-			const float e0 = e.d[0], e1 = e.d[1], e2 = e.d[2];
+			const bool skip = mode == kAdvRegion;
+			float e0 = d[0], e1 = d[1], e2 = d[2], q0 = rd[0], q1 = rd[1], q2 = rd[2];
+			if constexpr (kLA) { if (jump) { e0 = sd[0]; e1 = sd[1]; e2 = sd[2]; q0 = srd[0]; q1 = srd[1]; q2 = srd[2]; } }
 			float n0, n1, n2;
 			if (mode == kAdvNext)
 			{
@@ -249,73 +366,87 @@ struct FlatRay
 			}
 			else
 			{
-				// cluster edge of the voxel of the failed test: (int)o for the original algorithm, gridValues in a jump
-				n0 = (float)cluster_edge(e0, jump ? g[0] : (int)o[0]);
-				n1 = (float)cluster_edge(e1, jump ? g[1] : (int)o[1]);
-				n2 = (float)cluster_edge(e2, jump ? g[2] : (int)o[2]);
+				// cluster edge of the voxel of the failed test ((int)o for the original algorithm, gridValues in a jump: g either
+				// way), or the region's far face +EPSILON / near face -EPSILON
+				const float lo = skip ? vsub(0.0f, kEps) : 0.0f, hi = skip ? vadd((float)kRegion, kEps) : 8.0f;
+				const uint32_t keep = skip ? 0u : ~7u;
+				n0 = vadd((float)(int)((uint32_t)g[0] & keep), e0 > 0.0f ? hi : lo);
+				n1 = vadd((float)(int)((uint32_t)g[1] & keep), e1 > 0.0f ? hi : lo);
+				n2 = vadd((float)(int)((uint32_t)g[2] & keep), e2 > 0.0f ? hi : lo);
 			}
 			float a0, a1, a2;
-			div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), e, a0, a1, a2);
+			div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), e0, e1, e2, q0, q1, q2, thr, a0, a1, a2);
+			// zero-direction guards exist only in the shadow routines of the ORIGINAL algorithm: its null-region skip
+			// (Renderer.cuh:191-193) and shadowRayMarchVoxelGrid (113-115,137-139,160-162), which also finishes a region for the
+			// longest-axis shadow routine (630); the longest-axis jump and null-region skip guard nothing (457-459, 650-652)
+			const bool gd = skip ? shadowOriginal() : (jump ? false : shadow());
 			if (gd) { a0 = (e0 != 0.0f) ? a0 : INFINITY; a1 = (e1 != 0.0f) ? a1 : INFINITY; a2 = (e2 != 0.0f) ? a2 : INFINITY; }
 			float m = min3(a0, a1, a2);
-			if (m == 0.0f && mode != kAdvNext)
+			if (m == 0.0f && (mode == kAdvCluster || jump))
 			{
 				// the ray sits on a cluster face it cannot leave: fast-forward the EPSILON crawl (crawl_skip, vrm_core.cuh)
-				const int skipped = crawl_skip(o, e, jump ? g[0] : (int)o[0], jump ? g[1] : (int)o[1], jump ? g[2] : (int)o[2]);
+				const float e[3] = {e0, e1, e2};
+				const int skipped = crawl_skip(o, e, thr, g[0], g[1], g[2]);
 				if (skipped > 0)
 				{
 					if (STATS) { c.st.nExist += skipped; c.st.nExistFalse += skipped; c.st.nCrawlSkipped += skipped; }
-					div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), e, a0, a1, a2);  // same cell, same edges; guards are moot on the fast path
+					div3(vsub(n0, o[0]), vsub(n1, o[1]), vsub(n2, o[2]), e0, e1, e2, q0, q1, q2, thr, a0, a1, a2);  // same cell, same edges; guards are moot on the fast path
 					m = min3(a0, a1, a2);
 				}
 			}
-			const float s = vadd(m, kEps);
-			if (mode == kAdvNext) { t0 = a0; t1 = a1; t2 = a2; tMin = m; }
-			if (jump) { t0 = a0; t1 = a1; t2 = a2; tMin = s; }
+			const float s = skip ? m : vadd(m, kEps);
+			if (mode == kAdvNext || jump)
+			{
+				// tX,tY,tZ,tMin of Renderer.cuh:273-277 (a cluster skip leaves them stale) / 713-716 (tMin including +EPSILON):
+				// all the normal ever asks is which of them equal tMin
+				const float tm = jump ? s : m;
+				fl = (fl & ~kFlEqMask) | (a0 == tm ? kFlEq0 : 0u) | (a1 == tm ? kFlEq0 << 1 : 0u) | (a2 == tm ? kFlEq0 << 2 : 0u);
+			}
 			o[0] = along(o[0], s, e0); o[1] = along(o[1], s, e1); o[2] = along(o[2], s, e2);
 			// grid_in_region((int)floorf(o)) of the jump (Renderer.cuh:719-723) and isRayInRegion(o) agree for every o
-			if (!ray_in_region(o)) { change_region(c); return; }
-			c0 = (int)o[0]; c1 = (int)o[1]; c2 = (int)o[2];  // == (int)floorf(o) inside a region
-			if (jump) { g[0] = c0; g[1] = c1; g[2] = c2; }
+			if (skip || !ray_in_region(o)) { change_region(c); return; }
+			g[0] = (int)o[0]; g[1] = (int)o[1]; g[2] = (int)o[2];  // == (int)floorf(o) inside a region
 		}
 		else
 		{
 			slot = (int)(seq & 3u);
 			seq >>= 2;
-			g[0] += slot == 0 ? ad[0] : 0;
-			g[1] += slot == 1 ? ad[1] : 0;
-			g[2] += slot == 2 ? ad[2] : 0;
-			c0 = g[0]; c1 = g[1]; c2 = g[2];
+			g[0] += slot == 0 ? (d[0] < 0.0f ? -1 : 1) : 0;
+			g[1] += slot == 1 ? ad1 : 0;
+			g[2] += slot == 2 ? ad2 : 0;
 		}
 
-		// the voxel test: doesVoxelSpaceExist + lookupVoxel
-		const bool e = space_exists(c, r, p, c0, c1, c2);
-		uint32_t col = kEmpty;
-		if (e) col = lookup_voxel(c, r, p, reg, c0, c1, c2);
+		uint32_t col;
+		const bool e = voxel_test(c, g[0], g[1], g[2], col);
 
 		if (col != kEmpty)
 		{
 			if (!test)
 			{
 				// original algorithm: Renderer.cuh:312-315; jump: Renderer.cuh:733-738 (tMin carries +EPSILON there, so the
-				// comparison normally falls through to the Z normal)
-				int nAxisW = normal_axis_from_t(p, t0, t1, t2, tMin);
-				float dn = p.axis(0) == nAxisW ? k.d[0] : (p.axis(1) == nAxisW ? k.d[1] : k.d[2]);  // scaled direction = s * d, s > 0: same sign
-				record_hit(col, o, nAxisW, copysignf(1.0f, -dn), jump);
+				// comparison normally falls through to the Z normal).  getNormalFromTValues tests X, then Y, else Z.
+				const PermRuntime p = unpack_perm(fl);
+				int mW = 0;
+				if (fl & kFlEq0) mW |= 1 << p.a0;
+				if (fl & (kFlEq0 << 1)) mW |= 1 << p.a1;
+				if (fl & (kFlEq0 << 2)) mW |= 1 << p.a2;
+				const int nAxisW = (mW & 1) ? 0 : ((mW & 2) ? 1 : 2);
+				const float dn = p.a0 == nAxisW ? d[0] : (p.a1 == nAxisW ? d[1] : d[2]);  // scaled direction = s * d, s > 0: same sign
+				record_hit(c, col, o[0], o[1], o[2], nAxisW, copysignf(1.0f, -dn), jump, g[0], g[1], g[2]);
 			}
 			else if constexpr (kLA)
 			{
-				float odS = pick3(slot, ko.d[0], ko.d[1], ko.d[2]);
-				float pos[3];
-				if (slot == 0) { pos[0] = ro[0]; pos[1] = ro[1]; pos[2] = ro[2]; }  // Renderer.cuh:899
-				else
+				const PermRuntime p = unpack_perm(fl);
+				const float odS = pick3(slot, sd[0], sd[1], sd[2]);
+				float p0 = ro[0], p1 = ro[1], p2 = ro[2];  // Renderer.cuh:899
+				if (slot != 0)
 				{
 					// getLocalHitLocation, Renderer.cuh:753-758
-					float ooS = pick3(slot, o[0], o[1], o[2]);
-					float tl = odS > 0.0f ? vdiv(vsub(ceilf(ooS), ooS), odS) : vdiv(vsub(floorf(ooS), ooS), odS);
-					pos[0] = along(o[0], tl, ko.d[0]); pos[1] = along(o[1], tl, ko.d[1]); pos[2] = along(o[2], tl, ko.d[2]);
+					const float ooS = pick3(slot, o[0], o[1], o[2]);
+					const float tl = odS > 0.0f ? vdiv(vsub(ceilf(ooS), ooS), odS) : vdiv(vsub(floorf(ooS), ooS), odS);
+					p0 = along(o[0], tl, sd[0]); p1 = along(o[1], tl, sd[1]); p2 = along(o[2], tl, sd[2]);
 				}
-				record_hit(col, pos, p.axis(slot), copysignf(1.0f, -odS), true);
+				record_hit(c, col, p0, p1, p2, p.axis(slot), copysignf(1.0f, -odS), true, g[0], g[1], g[2]);
 			}
 			return;
 		}
@@ -330,11 +461,11 @@ struct FlatRay
 				{
 					// the jump reached a cluster that exists but the voxel is empty: re-snap to the longest axis and `continue`
 					// the while loop (Renderer.cuh:742-750)
-					float tNext = div1(vsub(ko.d[0] > 0.0f ? ceilf(o[0]) : floorf(o[0]), o[0]), ko, 0);
-					float tt = vadd(tNext, kEps);
-					ro[0] = along(o[0], tt, ko.d[0]); ro[1] = along(o[1], tt, ko.d[1]); ro[2] = along(o[2], tt, ko.d[2]);
-					ad[1] = (int)ro[1] - g[1];
-					ad[2] = (int)ro[2] - g[2];
+					const float tNext = div1(vsub(sd[0] > 0.0f ? ceilf(o[0]) : floorf(o[0]), o[0]), sd[0], srd[0], thr);
+					const float tt = vadd(tNext, kEps);
+					ro[0] = along(o[0], tt, sd[0]); ro[1] = along(o[1], tt, sd[1]); ro[2] = along(o[2], tt, sd[2]);
+					ad1 = (int)ro[1] - g[1];
+					ad2 = (int)ro[2] - g[2];
 					st = kStHead;
 				}
 			}
@@ -350,28 +481,25 @@ struct FlatRay
 				if (STATS) { c.st.nExist++; c.st.nExistFalse++; }
 				mode = kAdvJump;
 			}
-			else if (--nTests == 0)
+			else if (slot == 0)
 			{
-				// Renderer.cuh:903-908
+				// the longest axis was this iteration's last test: Renderer.cuh:903-908
 				o[0] = ro[0]; o[1] = ro[1]; o[2] = ro[2];
-				ro[0] = vadd(ro[0], ko.d[0]); ro[1] = vadd(ro[1], ko.d[1]); ro[2] = vadd(ro[2], ko.d[2]);
-				ad[1] = (int)ro[1] - g[1];
-				ad[2] = (int)ro[2] - g[2];
+				ro[0] = vadd(ro[0], sd[0]); ro[1] = vadd(ro[1], sd[1]); ro[2] = vadd(ro[2], sd[2]);
+				ad1 = (int)ro[1] - g[1];
+				ad2 = (int)ro[2] - g[2];
 				st = kStHead;
 			}
 		}
 	}
 
-	// Run the block of the current state.  Returns true when the pixel is resolved.
+	// Run the blocks the ray's state asks for, in program order.  Returns true when the pixel is resolved.
 	VRM_HD bool step(RayCtx<ST, STATS>& c)
 	{
+		if (st == kStHit) do_hit(c);
 		if (st == kStRegion) do_region(c);
-		else if (st == kStHit) do_hit(c);
-		else
-		{
-			if constexpr (kLA) { if (st == kStHead) do_head(); }
-			if (st == kStMain) do_main(c);
-		}
+		if constexpr (kLA) { if (st == kStHead) do_head(); }
+		if (st == kStMain) do_main(c);
 		return st == kStDone;
 	}
 };

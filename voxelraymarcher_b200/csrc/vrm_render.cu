@@ -15,8 +15,16 @@ using namespace vrm;
 namespace
 {
 
+// Tunables (A/B builds: make VARIANT_FLAGS=-DVRM_... OUT=...; the defaults are the measured choices)
+#ifndef VRM_BLOCK_TILES_Y
+#define VRM_BLOCK_TILES_Y 2
+#endif
+#ifndef VRM_FLAT_LA_MINBLOCKS
+#define VRM_FLAT_LA_MINBLOCKS 4
+#endif
+
 constexpr int kTileW = 8, kTileH = 4;          // pixels per warp
-constexpr int kBlockTilesX = 4, kBlockTilesY = 2;
+constexpr int kBlockTilesX = 4, kBlockTilesY = VRM_BLOCK_TILES_Y;
 constexpr int kBlockW = kTileW * kBlockTilesX;  // 32
 constexpr int kBlockH = kTileH * kBlockTilesY;  // 8
 constexpr int kRenderThreads = kBlockW * kBlockH;  // resident CTAs per SM: 4 (<= 64 registers); 5 for hashtable + longest axis, which measured faster at 48 registers / 40 warps
@@ -25,6 +33,7 @@ struct RenderArgs
 {
 	SceneView sv;
 	Lighting light;
+	LightWalk lw;
 	float translation[3];
 	float scale;
 	const float* cams;  // nViews x 15
@@ -55,7 +64,7 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 }
 
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
-__global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOriginal) ? 4 : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) render_kernel(const RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) * 2 / VRM_BLOCK_TILES_Y) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lx = (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1)), ly = (warp / kBlockTilesX) * kTileH + (lane / kTileW);
@@ -69,6 +78,8 @@ __global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOrig
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
 	uint32_t color = 0;
@@ -82,9 +93,21 @@ __global__ void __launch_bounds__(kRenderThreads, (FLATLOOP && ALGO != kAlgoOrig
 		primary_ray(camv, x, y, a.W, a.H, o, d);
 		// FLATLOOP: the same tile mapping, but each lane runs the state machine of vrm_flat.cuh (one voxel test per iteration
 		// of a single loop) instead of the nested loops of vrm_core.cuh
-		color = FLATLOOP ? march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale) : march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
-		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
-		if (a.hits) reinterpret_cast<int4*>(a.hits)[p] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+		if constexpr (FLATLOOP)
+		{
+			if (a.hits)
+			{
+				// the hit map slot is cleared here and filled at the hit site (record_hit_voxel)
+				c.hitOut = a.hits + 4 * (((size_t)blockIdx.z * a.H + y) * a.W + x);
+				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+			}
+			color = march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale);
+		}
+		else
+		{
+			color = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+			if (a.hits) reinterpret_cast<int4*>(a.hits)[((size_t)blockIdx.z * a.H + y) * a.W + x] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+		}
 	}
 	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
 	const bool wholeBlock = x0 + kBlockW <= a.W && y0 + kBlockH <= a.yEnd && a.rowWordsOk;
@@ -127,6 +150,8 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
 	FlatRay<ST, ALGO, STATS> ray;
@@ -170,13 +195,16 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 						for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
 						float o[3], d[3];
 						primary_ray(camv, x, y, a.W, a.H, o, d);
-						c.hit[0] = c.hit[1] = c.hit[2] = c.hit[3] = 0;
 						pixel = ((size_t)view * a.H + y) * a.W + x;
+						if (a.hits)
+						{
+							c.hitOut = a.hits + 4 * pixel;
+							*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+						}
 						ray.start_primary(c, o, d, a.scale);
 						if (ray.st == kStDone)  // missed the scene's bounding cube altogether
 						{
 							a.rgb[3 * pixel] = 0; a.rgb[3 * pixel + 1] = 0; a.rgb[3 * pixel + 2] = 0;
-							if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(0, 0, 0, 0);
 						}
 					}
 				}
@@ -196,7 +224,6 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 				a.rgb[3 * pixel] = (uint8_t)(color >> 16);
 				a.rgb[3 * pixel + 1] = (uint8_t)((color >> 8) & 0xFF);
 				a.rgb[3 * pixel + 2] = (uint8_t)(color & 0xFF);
-				if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 			}
 		}
 	}
@@ -207,6 +234,7 @@ struct TraceArgs
 {
 	SceneView sv;
 	Lighting light;
+	LightWalk lw;
 	float translation[3];
 	float scale;
 	const float* rays;  // n x 6
@@ -223,14 +251,28 @@ __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
 	if (i < a.n)
 	{
 		float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
 		float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
-		a.colour[i] = FLATLOOP ? march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale) : march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
-		if (a.hits) reinterpret_cast<int4*>(a.hits)[i] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+		if constexpr (FLATLOOP)
+		{
+			if (a.hits)
+			{
+				c.hitOut = a.hits + 4 * i;
+				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+			}
+			a.colour[i] = march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale);
+		}
+		else
+		{
+			a.colour[i] = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+			if (a.hits) reinterpret_cast<int4*>(a.hits)[i] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+		}
 	}
 	flush_stats<STATS>(c, a.stats);
 }
@@ -265,6 +307,7 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 {
 	a.sv = s->view();
 	a.light = s->light;
+	a.lw = make_light_walk(s->light);  // host, IEEE fp32 without contraction (-fmad=false / -ffp-contract=off): the values the kernel would compute
 	a.translation[0] = translation[0]; a.translation[1] = translation[1]; a.translation[2] = translation[2];
 	a.scale = static_cast<float>(scale);  // Ray.cuh:16
 	a.stats = s->statsEnabled ? s->d_stats : nullptr;
