@@ -75,7 +75,8 @@ void render_rows(const SimScene& s, const float* cam, const float* tr, float sca
 			{
 				float o[3], d[3];
 				c.reset();
-				primary_ray(cam, x, (uint32_t)y, W, H, o, d);
+				if (gFlat) primary_ray_flat(cam, x, (uint32_t)y, W, H, 1.0f / (float)W, 1.0f / (float)H, o, d);  // what the state-machine kernels run
+				else primary_ray(cam, x, (uint32_t)y, W, H, o, d);
 				uint32_t color = march<ST, ALGO>(c, o, d, scale);
 				size_t p = (size_t)y * W + x;
 				rgb[3 * p] = (uint8_t)(color >> 16); rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF); rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
@@ -128,6 +129,42 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 extern "C" {
 
 void sim_set_flat(int flat) { gFlat = flat; }
+
+// primary_ray_flat's image-plane divisions against IEEE division: every pixel coordinate of an image side of n pixels.
+// Returns the number of mismatches (0 expected).
+uint64_t sim_check_image_division(uint32_t n)
+{
+	uint64_t bad = 0;
+	const float fn = (float)n, inv = 1.0f / fn;
+	for (uint32_t x = 0; x <= n; x++)
+	{
+		const float num = vadd((float)x, 0.5f);
+		const float q = div_by_const(num, fn, inv), ref = num / fn;
+		if (memcmp(&q, &ref, 4) != 0) bad++;
+	}
+	return bad;
+}
+
+// div3 (reciprocal + FMA residual form with its slow-path guard) against IEEE division for count pseudo-random numerator
+// triples divided by one common denominator (the ray-length normalisation of primary_ray_flat).
+uint64_t sim_check_common_division(uint32_t seed, uint64_t count)
+{
+	uint64_t bad = 0, st = seed * 0x9E3779B97F4A7C15ull + 1;
+	auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (uint32_t)(st >> 16); };
+	for (uint64_t i = 0; i < count; i++)
+	{
+		float x[3], len;
+		for (int k = 0; k < 3; k++) { uint32_t b = (next() & 0x807FFFFFu) | ((100u + next() % 40u) << 23); memcpy(&x[k], &b, 4); }
+		{ uint32_t b = (next() & 0x007FFFFFu) | ((110u + next() % 30u) << 23); memcpy(&len, &b, 4); }
+		if (i % 7 == 0) x[i % 3] = 0.0f;
+		const float rl = vrcp(len);
+		const float thr = dir_component_safe(len) ? 7.888609052210118e-31f : NAN;
+		float q[3];
+		div3(x[0], x[1], x[2], len, len, len, rl, rl, rl, thr, q[0], q[1], q[2]);
+		for (int k = 0; k < 3; k++) { const float ref = x[k] / len; if (memcmp(&q[k], &ref, 4) != 0) bad++; }
+	}
+	return bad;
+}
 unsigned long long sim_crawl_skipped() { unsigned long long v = gCrawlSkipped; gCrawlSkipped = 0; return v; }
 void* sim_scene_create() { return new SimScene(); }
 void sim_scene_destroy(void* h) { delete static_cast<SimScene*>(h); }
@@ -183,6 +220,8 @@ int sim_scene_build(void* h, int storageType)
 		}
 		uint32_t running = (uint32_t)(s->values.size() - kv.second.size());
 		for (uint32_t w = 0; w < 512 * 16; w++) { hdr[w].y = running; running += (uint32_t)__builtin_popcount(hdr[w].x); }
+		for (uint32_t w = 0; w < 512 * 16; w++)
+			if ((s->clusterMask[(size_t)ri * 16 + (w >> 9)] >> ((w >> 4) & 31)) & 1u) hdr[w].y |= kHeaderClusterExists;
 		// cuckoo: sequential insertion with the product's hash functions
 		uint32_t N = (uint32_t)kv.second.size();
 		HashRegionDesc d;

@@ -127,3 +127,17 @@ def test_core_crawl_fast_forward_is_bit_exact(algo):
     assert int(ta["counters"][0]) > 10_000_000          # the reference really does crawl here
     for k in ("colour", "hits", "counters"):
         assert np.array_equal(ta[k], tb[k]), k
+
+
+def test_exact_reciprocal_divisions_of_the_primary_ray():
+    """primary_ray_flat replaces (x + 0.5) / W, (H - y + 0.5) / H and rel / len by reciprocal + FMA-residual divisions: they must
+    be the IEEE quotients, bit for bit, for every pixel coordinate of the image sizes in use and for random normalisations."""
+    import ctypes as C
+    lib = po._lib("sim")
+    lib.sim_check_image_division.restype = C.c_uint64
+    lib.sim_check_image_division.argtypes = [C.c_uint32]
+    lib.sim_check_common_division.restype = C.c_uint64
+    lib.sim_check_common_division.argtypes = [C.c_uint32, C.c_uint64]
+    for n in (1, 2, 3, 7, 72, 128, 144, 180, 256, 320, 360, 540, 640, 720, 960, 1000, 1080, 1280, 1920, 2160, 3840, 4096, 7680, 65535, 1 << 20):
+        assert lib.sim_check_image_division(n) == 0, n
+    assert lib.sim_check_common_division(1, 20_000_000) == 0

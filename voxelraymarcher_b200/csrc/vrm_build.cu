@@ -270,6 +270,22 @@ __global__ void vcs_fill_kernel(const unsigned long long* __restrict__ ukeys, co
 	if (firstOfCluster) atomicOr(clusterMask + (size_t)ri * 16 + (cid >> 5), 1u << (cid & 31));
 }
 
+// Every occupancy word of a cluster that holds at least one voxel carries kHeaderClusterExists in its colour index, so that one
+// 8-byte header load answers doesClusterExist AND the occupancy test (vrm_flat.cuh voxel_test).  One thread per cluster.
+__global__ void vcs_flag_clusters_kernel(uint2* __restrict__ headers, const uint32_t* __restrict__ clusterMask, uint64_t numClusters)
+{
+	uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (c >= numClusters) return;
+	if (!((clusterMask[c >> 5] >> (c & 31)) & 1u)) return;
+	uint4* words = reinterpret_cast<uint4*>(headers + c * 16);
+	for (int w = 0; w < 8; w++)
+	{
+		uint4 v = words[w];
+		v.y |= kHeaderClusterExists; v.w |= kHeaderClusterExists;
+		words[w] = v;
+	}
+}
+
 // ---- 6b. cuckoo hash table -------------------------------------------------------------------------------------
 __global__ void fill_slots_kernel(unsigned long long* __restrict__ slots, uint64_t n)
 {
@@ -429,12 +445,16 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 	if (storageType == VRM_STORAGE_VCS)
 	{
 		const size_t headerBytes = (size_t)numRegions * 512 * 16 * sizeof(uint2);
+		// 31-bit colour indices (the top bit of a header's index word is the cluster-exists flag), 32-bit header word indices
+		if (unique >= (1ull << 31) || (uint64_t)numRegions * 8192ull >= (1ull << 32)) { s->lastError = "scene too large for the VCS index widths"; return VRM_ERR_INVALID; }
 		if (headers.alloc(headerBytes) != cudaSuccess || clusterMask.alloc((size_t)numRegions * 16 * 4) != cudaSuccess)
 		{ cudaGetLastError(); s->lastError = "VCS allocation failed"; return VRM_ERR_NOMEM; }
 		VRM_CUDA(s, cudaMemsetAsync(headers.p, 0, headerBytes, st));
 		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4, st));
 		if (unique)
 			vcs_fill_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), regionOf.as<uint32_t>(), unique, headers.as<uint2>(), clusterMask.as<uint32_t>());
+		if (unique)
+			vcs_flag_clusters_kernel<<<grid_for((uint64_t)numRegions * 512), kThreads, 0, st>>>(headers.as<uint2>(), clusterMask.as<uint32_t>(), (uint64_t)numRegions * 512);
 		VRM_CUDA(s, cudaGetLastError());
 		bytes += headerBytes + (size_t)numRegions * 64 + unique * 4;
 	}

@@ -40,6 +40,7 @@ constexpr int kRegion = 64;                    // BLOCK_SIZE, geometry/VoxelFunc
 constexpr int kStorageVcs = 0, kStorageHash = 1;  // StorageType, geometry/VoxelFunctions.cuh:37
 constexpr int kAlgoLongestAxis = 0, kAlgoOriginal = 1;  // main/Main.cu:58-68
 constexpr unsigned long long kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kHeaderClusterExists = 0x80000000u;  // VCS header word, .y: the word's cluster holds at least one voxel (low 31 bits: index of the word's first colour)
 
 // ---------------------------------------------------------------- non-contracting fp32
 
@@ -380,7 +381,7 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		uint32_t code = ((uint32_t)(g0 & 7) << p.cs(0)) | ((uint32_t)(g1 & 7) << p.cs(1)) | ((uint32_t)(g2 & 7) << p.cs(2));
 		uint2 h = ldg(c.sv.headers + (((size_t)rv.ri * 512 + cid) * 16 + (code >> 5)));
 		uint32_t bit = code & 31;
-		if ((h.x >> bit) & 1u) v = ldg(c.sv.values + h.y + popc32(h.x & ((1u << bit) - 1u)));
+		if ((h.x >> bit) & 1u) v = ldg(c.sv.values + (h.y & ~kHeaderClusterExists) + popc32(h.x & ((1u << bit) - 1u)));
 	}
 	if (STATS) c.st.nLookup++;
 	if (v != kEmpty)

@@ -28,6 +28,12 @@
 
 #include "vrm_core.cuh"
 
+// 1: the state machine's VCS test site reads the cluster-exists flag from the header word it needs anyway (one load);
+// 0: separate 64-byte-per-region cluster mask first (two dependent loads, but empty clusters never touch the headers)
+#ifndef VRM_VCS_FUSED_EXIST
+#define VRM_VCS_FUSED_EXIST 1
+#endif
+
 namespace vrm
 {
 
@@ -82,6 +88,40 @@ VRM_HD LightWalk make_light_walk(const Lighting& L)
 	w.laThr = (k.thr == k.thr && ko.thr == ko.thr) ? k.thr : NAN;
 	w.laPerm = pack_perm(p);
 	return w;
+}
+
+// apply_lighting's directional branch with the three colour / 255.0f divisions done by the exact reciprocal + FMA residual
+// form (div_by_const; checked equal to IEEE division for every integer numerator up to 2^24).  Same values, a third of the
+// instructions.  The point-light branch is the shared apply_lighting.
+VRM_HD uint32_t apply_lighting_flat(const Lighting& L, const float* translation, uint32_t voxelColor, int normalAxis, float normalSign,
+                                    const float* hitLocal, const int* regW)
+{
+	if (L.usePoint) return apply_lighting(L, translation, voxelColor, normalAxis, normalSign, hitLocal, regW);
+	const float r255 = 0.00392156886f;  // RN(1 / 255)
+	const float cr = div_by_const((float)(voxelColor >> 16), 255.0f, r255);
+	const float cg = div_by_const((float)((voxelColor >> 8) & 0xFF), 255.0f, r255);
+	const float cb = div_by_const((float)(voxelColor & 0xFF), 255.0f, r255);
+	const float n0 = normalAxis == 0 ? normalSign : 0.0f, n1 = normalAxis == 1 ? normalSign : 0.0f, n2 = normalAxis == 2 ? normalSign : 0.0f;
+	const float diff = fmaxf(vadd(vadd(vmul(n0, L.dir[0]), vmul(n1, L.dir[1])), vmul(n2, L.dir[2])), 0.0f);  // Renderer.cuh:57-66
+	return vec_to_rgb(vmul(cr, vmul(diff, L.color[0])), vmul(cg, vmul(diff, L.color[1])), vmul(cb, vmul(diff, L.color[2])));
+}
+
+// primary_ray with its five divisions (two by the image size, three by the ray length) in the exact reciprocal form.
+// invW / invH = RN(1 / W), RN(1 / H) from the host.
+VRM_HD void primary_ray_flat(const float* cam, uint32_t x, uint32_t y, uint32_t W, uint32_t H, float invW, float invH, float* o, float* d)
+{
+	const float u = div_by_const(vadd((float)x, 0.5f), (float)W, invW);  // numerators >= 0.5, 1 <= W,H < 2^32: inside div_by_const's preconditions
+	const float v = div_by_const(vadd((float)(H - y), 0.5f), (float)H, invH);
+	float rel[3];
+	for (int i = 0; i < 3; i++)
+	{
+		o[i] = vadd(vadd(cam[3 + i], vmul(u, cam[6 + i])), vmul(v, cam[9 + i]));
+		rel[i] = vsub(o[i], cam[i]);
+	}
+	const float len = vsqrt(vadd(vadd(vmul(rel[0], rel[0]), vmul(rel[1], rel[1])), vmul(rel[2], rel[2])));
+	const float rl = vrcp(len);
+	const float thr = dir_component_safe(len) ? 7.888609052210118e-31f : NAN;
+	div3(rel[0], rel[1], rel[2], len, len, len, rl, rl, rl, thr, d[0], d[1], d[2]);
 }
 
 template <int ST, int ALGO, bool STATS>
@@ -237,7 +277,7 @@ struct FlatRay
 			const int reg[3] = {(int)ur[0] + minC, (int)ur[1] + minC, (int)ur[2] + minC};
 			to_world(p, ro, hitW); to_world(p, reg, regW);
 		}
-		result = apply_lighting(c.light, c.translation, result, nAxisW, nSign, hitW, regW);
+		result = apply_lighting_flat(c.light, c.translation, result, nAxisW, nSign, hitW, regW);
 		if (!c.light.useShadows) { finish(result); return; }
 		fl = kFlShadow | (laKind ? kFlShadowLA : 0u);
 		PermRuntime p;
@@ -335,14 +375,22 @@ struct FlatRay
 			// One value carries both codes: cc = cluster id << 9 | in-cluster code.  A coordinate v in [0, 64) contributes
 			// (v & 7) | (v >> 3) << 9 = (v * 65) & 0xE07, shifted to its axis' place.
 			const uint32_t cc = ((((uint32_t)c0 * 65u) & 0xE07u) << sh[0]) | ((((uint32_t)c1 * 65u) & 0xE07u) << sh[1]) | ((((uint32_t)c2 * 65u) & 0xE07u) << sh[2]);
+			// header word index inside the region = cid * 16 + code / 32 = cc >> 5; bit = code % 32 = cc % 32
+#if VRM_VCS_FUSED_EXIST
+			// ONE 8-byte load answers both questions: the word's .y carries the cluster-exists flag (vrm_build.cu)
+			const uint2 h = ldg(c.sv.headers + ((uint32_t)ri * 8192u + (cc >> 5)));
+			const bool e = (h.y & kHeaderClusterExists) != 0;
+			if (STATS) { c.st.nExist++; if (!e) c.st.nExistFalse++; }
+			if (!e) return false;
+#else
 			const uint32_t cid = cc >> 9;
 			const bool e = (ldg(c.sv.clusterMask + ((uint32_t)ri * 16u + (cid >> 5))) >> (cid & 31u)) & 1u;
 			if (STATS) { c.st.nExist++; if (!e) c.st.nExistFalse++; }
 			if (!e) return false;
-			// header word index inside the region = cid * 16 + code / 32 = cc >> 5; bit = code % 32 = cc % 32
 			const uint2 h = ldg(c.sv.headers + ((uint32_t)ri * 8192u + (cc >> 5)));
+#endif
 			const uint32_t bit = cc & 31u;
-			if ((h.x >> bit) & 1u) col = ldg(c.sv.values + (h.y + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
+			if ((h.x >> bit) & 1u) col = ldg(c.sv.values + ((h.y & ~kHeaderClusterExists) + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
 			if (STATS) { c.st.nLookup++; if (col != kEmpty) c.st.nLookupHit++; }
 			return true;
 		}

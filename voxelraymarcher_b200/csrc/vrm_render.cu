@@ -19,12 +19,18 @@ namespace
 #ifndef VRM_BLOCK_TILES_Y
 #define VRM_BLOCK_TILES_Y 1
 #endif
+#ifndef VRM_BLOCK_TILES_X
+#define VRM_BLOCK_TILES_X 4
+#endif
+#ifndef VRM_WARP_STORE
+#define VRM_WARP_STORE 0
+#endif
 #ifndef VRM_FLAT_LA_MINBLOCKS
 #define VRM_FLAT_LA_MINBLOCKS 4
 #endif
 
 constexpr int kTileW = 8, kTileH = 4;          // pixels per warp
-constexpr int kBlockTilesX = 4, kBlockTilesY = VRM_BLOCK_TILES_Y;
+constexpr int kBlockTilesX = VRM_BLOCK_TILES_X, kBlockTilesY = VRM_BLOCK_TILES_Y;
 constexpr int kBlockW = kTileW * kBlockTilesX;  // 32
 constexpr int kBlockH = kTileH * kBlockTilesY;  // 8
 constexpr int kRenderThreads = kBlockW * kBlockH;  // 128 threads = a 32x4 pixel row of four tiles: measured 2.5-3 % faster than 32x8 for every combination (fewer warps parked at the CTA barrier behind a slow tile)
@@ -38,6 +44,7 @@ struct RenderArgs
 	float scale;
 	const float* cams;  // nViews x 15
 	uint32_t W, H;
+	float invW, invH;      // RN(1 / W), RN(1 / H) (host): exact division by a constant in primary_ray_flat
 	uint32_t rowWordsOk;   // 1 when every 32-pixel row segment starts on a 4-byte boundary (W * 3 % 4 == 0 and an aligned base)
 	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
 	uint8_t* rgb;       // nViews x H x W x 3
@@ -64,7 +71,7 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 }
 
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
-__global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) * 2 / VRM_BLOCK_TILES_Y) render_kernel(const RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lx = (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1)), ly = (warp / kBlockTilesX) * kTileH + (lane / kTileW);
@@ -90,7 +97,8 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 #pragma unroll
 		for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
 		float o[3], d[3];
-		primary_ray(camv, x, y, a.W, a.H, o, d);
+		if constexpr (FLATLOOP) primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
+		else primary_ray(camv, x, y, a.W, a.H, o, d);
 		// FLATLOOP: the same tile mapping, but each lane runs the state machine of vrm_flat.cuh (one voxel test per iteration
 		// of a single loop) instead of the nested loops of vrm_core.cuh
 		if constexpr (FLATLOOP)
@@ -110,6 +118,24 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		}
 	}
 	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
+#if VRM_WARP_STORE
+	// per-warp staging: each warp writes its own 8x4 tile as four 24-byte row segments, no CTA barrier
+	const uint32_t tx0 = x0 + (warp % kBlockTilesX) * kTileW, ty0 = y0 + (warp / kBlockTilesX) * kTileH;
+	const bool wholeTile = tx0 + kTileW <= a.W && ty0 + kTileH <= a.yEnd && a.rowWordsOk;
+	if (wholeTile)
+	{
+		uint32_t (*mine)[kTileW * 3 / 4] = reinterpret_cast<uint32_t (*)[kTileW * 3 / 4]>(&staged[0][0]) + warp * kTileH;
+		uint8_t* sb = reinterpret_cast<uint8_t*>(&mine[lane / kTileW][0]) + (lane & (kTileW - 1)) * 3;
+		sb[0] = (uint8_t)(color >> 16); sb[1] = (uint8_t)((color >> 8) & 0xFF); sb[2] = (uint8_t)(color & 0xFF);
+		__syncwarp();
+		if (lane < kTileH * (kTileW * 3 / 4))
+		{
+			const uint32_t row = lane / (kTileW * 3 / 4), w = lane % (kTileW * 3 / 4);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + (((size_t)blockIdx.z * a.H + ty0 + row) * a.W + tx0) * 3);
+			dst[w] = mine[row][w];
+		}
+	}
+#else
 	const bool wholeBlock = x0 + kBlockW <= a.W && y0 + kBlockH <= a.yEnd && a.rowWordsOk;
 	if (wholeBlock)
 	{
@@ -123,6 +149,7 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 			dst[w] = staged[row][w];
 		}
 	}
+#endif
 	else if (inside)
 	{
 		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
@@ -373,6 +400,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	RenderArgs a;
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
+	a.invW = 1.0f / (float)W; a.invH = 1.0f / (float)H;
 	a.yBase = yBase; a.yEnd = yEnd;
 	a.rowWordsOk = ((W * 3u) % 4u == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 3u) == 0 && (((size_t)W * H * 3) % 4 == 0 || nViews == 1)) ? 1u : 0u;
 	a.queue = s->d_queue;
