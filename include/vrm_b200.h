@@ -80,6 +80,14 @@ int vrm_scene_synchronize(vrm_scene* scene);
 int vrm_scene_add_voxels(vrm_scene* scene, const int32_t* xyz, const uint32_t* rgb, uint64_t n);
 int vrm_scene_add_voxels_device(vrm_scene* scene, const int32_t* d_xyz, const uint32_t* d_rgb, uint64_t n);
 
+/* Procedural scenes generated ON THE GPU straight into the staging list (no host copy of the voxels; SURVEY.md 8f-3;
+ * the reference's own generators are host loops calling insertVoxel: geometry/VoxelCube.cuh:10-39, VoxelSphere.cuh:10-66).
+ * The voxel sets and colours are those of voxelraymarcher_b200/scenes.py terrain() / sparse_shells() -- the synthetic
+ * workloads of BASELINE.json configs 3-5.  max_height 0 = size.  n_out (nullable) receives the number of voxels added.
+ * Legal only before vrm_scene_build; can be mixed with vrm_scene_add_voxels. */
+int vrm_scene_generate_terrain(vrm_scene* scene, uint32_t size, uint32_t seed, uint32_t max_height, uint64_t* n_out);
+int vrm_scene_generate_sparse_shells(vrm_scene* scene, uint32_t size, uint32_t cell, uint32_t seed, uint32_t fill_pct, uint64_t* n_out);
+
 /* Build the chosen structure ON THE GPU (radix sort -> last-wins dedupe -> region directory ->
  * VCS cluster tables or cuckoo insertion).  build_ms (nullable) receives the device time. */
 int vrm_scene_build(vrm_scene* scene, int storage_type, float* build_ms);

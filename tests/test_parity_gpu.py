@@ -293,3 +293,36 @@ def test_crawl_fast_forward_is_bit_exact(algo):
     assert np.array_equal(got["hits"], want["hits"])
     assert [st["exist_checks"], st["exist_false"], st["lookups"], st["lookup_hits"]] == [int(v) for v in want["counters"][:4]]
     assert st["crawl_skipped"] > 10_000_000
+
+
+@pytest.mark.parametrize("storage", ["vcs", "hashtable"])
+@pytest.mark.parametrize("kind,kw", [("terrain", dict(size=192, seed=1234)), ("terrain", dict(size=96, seed=5, max_height=40)),
+                                      ("shells", dict(size=256, cell=64, seed=7, fill_pct=50)), ("shells", dict(size=192, cell=32, seed=11, fill_pct=35))])
+def test_gpu_scene_generators_match_host_generators(kind, kw, storage):
+    """vrm_scene_generate_* put the same voxel set with the same colours into the staging list as scenes.terrain /
+    scenes.sparse_shells: same structure geometry, every host-generated voxel found with its colour, same voxel count
+    (so nothing extra), and a rendered frame that is bit-identical to the one of the host-generated scene."""
+    xyz, rgb = scenes.terrain(**kw) if kind == "terrain" else scenes.sparse_shells(**kw)
+    host = api.VoxelScene(0)
+    host.add_voxels(xyz, rgb)
+    host.generate_voxel_scene(storage)
+    dev = api.VoxelScene(0)
+    n = dev.generate_terrain(kw["size"], kw["seed"], kw.get("max_height", 0)) if kind == "terrain" else dev.generate_sparse_shells(kw["size"], kw["cell"], kw["seed"], kw["fill_pct"])
+    assert n == xyz.shape[0]
+    dev.generate_voxel_scene(storage)
+    ih, idv = host.info(), dev.info()
+    for k in ("diameter", "min_coord", "filled", "unique_voxels"):
+        assert ih[k] == idv[k], k
+    col, exists = dev.lookup(xyz)
+    assert np.array_equal(col, rgb)
+    q = lookup_queries(xyz, 20000, seed=3)
+    a, b = host.lookup(q), dev.lookup(q)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    size = kw["size"]
+    cam = api.Camera((-0.2 * size, 0.7 * size, -0.19 * size), (0.5 * size, 0.12 * size, 0.5 * size), (0.0, 1.0, 0.0), 60.0, np.float32(320) / np.float32(180))
+    for algo in ("original", "longestaxis"):
+        ra, rb = host.render(320, 180, algo, cam, want_hits=True), dev.render(320, 180, algo, cam, want_hits=True)
+        assert np.array_equal(ra["rgb"], rb["rgb"]) and np.array_equal(ra["hits"], rb["hits"])
+        assert int(ra["hits"][..., 3].sum()) > 1000
+    host.close()
+    dev.close()

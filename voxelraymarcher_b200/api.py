@@ -31,6 +31,7 @@ EMPTY = 1 << 30                                # EMPTY_KEY / EMPTY_VAL
 EXPORTS = [
     "vrm_error_string", "vrm_last_error", "vrm_device_available", "vrm_device_count", "vrm_device_name", "vrm_scene_create", "vrm_scene_destroy",
     "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
+    "vrm_scene_generate_terrain", "vrm_scene_generate_sparse_shells",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
     "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
@@ -67,6 +68,8 @@ def load_library():
         "vrm_scene_synchronize": (ci, [vp]),
         "vrm_scene_add_voxels": (ci, [vp, vp, vp, u64]),
         "vrm_scene_add_voxels_device": (ci, [vp, vp, vp, u64]),
+        "vrm_scene_generate_terrain": (ci, [vp, u32, u32, u32, C.POINTER(u64)]),
+        "vrm_scene_generate_sparse_shells": (ci, [vp, u32, u32, u32, u32, C.POINTER(u64)]),
         "vrm_scene_build": (ci, [vp, ci, C.POINTER(f32)]),
         "vrm_scene_info": (ci, [vp, C.POINTER(u32), C.POINTER(i32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
         "vrm_set_lighting": (ci, [vp, vp, vp, vp, ci, ci]),
@@ -189,6 +192,18 @@ class VoxelScene:
 
     def add_voxels_device(self, d_xyz_ptr: int, d_rgb_ptr: int, n: int):
         self._check(self.lib.vrm_scene_add_voxels_device(self.h, C.c_void_p(d_xyz_ptr), C.c_void_p(d_rgb_ptr), n), "vrm_scene_add_voxels_device")
+
+    def generate_terrain(self, size: int = 512, seed: int = 1234, max_height: int = 0) -> int:
+        """``scenes.terrain(size, seed, max_height)`` generated on the GPU straight into the staging list; returns the voxel count."""
+        n = C.c_uint64()
+        self._check(self.lib.vrm_scene_generate_terrain(self.h, size, seed, max_height, C.byref(n)), "vrm_scene_generate_terrain")
+        return int(n.value)
+
+    def generate_sparse_shells(self, size: int = 1024, cell: int = 64, seed: int = 7, fill_pct: int = 35) -> int:
+        """``scenes.sparse_shells(size, cell, seed, fill_pct)`` generated on the GPU straight into the staging list."""
+        n = C.c_uint64()
+        self._check(self.lib.vrm_scene_generate_sparse_shells(self.h, size, cell, seed, fill_pct, C.byref(n)), "vrm_scene_generate_sparse_shells")
+        return int(n.value)
 
     def generate_voxel_scene(self, storage_type):
         st = STORAGE[storage_type] if isinstance(storage_type, str) else int(storage_type)

@@ -20,6 +20,10 @@
 // Only key -> colour (last insert wins) and cluster occupancy are observable through the lookup seam, so the
 // layouts are free (SURVEY.md §7 hard part 4).
 #include "vrm_internal.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "../../include/vrm_b200.h"
 
 #include <algorithm>
@@ -48,6 +52,23 @@ struct DeviceBuf
 	void* release() { void* q = p; p = nullptr; return q; }
 };
 
+// All scratch of one build comes out of ONE device allocation: a dozen cudaMalloc / cudaFree pairs of hundreds of megabytes
+// cost several times the 3-4 ms the kernels of a 32 M voxel build take.
+struct Arena
+{
+	char* base = nullptr;
+	size_t cap = 0, off = 0;
+	~Arena() { if (base) cudaFree(base); }
+	static size_t pad(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+	cudaError_t reserve(size_t bytes) { cap = bytes; off = 0; return cudaMalloc(&base, bytes ? bytes : 256); }
+	template <class T> T* take(size_t count)
+	{
+		T* p = reinterpret_cast<T*>(base + off);
+		off += pad(count * sizeof(T));
+		return off <= cap ? p : nullptr;
+	}
+};
+
 __device__ __forceinline__ int floor_div64(int v) { return v >> 6; }  // == floorf(v / 64.0f) for |v| < 2^24 (VoxelSceneCPU.cuh:19-21)
 
 // ---- 1. region extent ------------------------------------------------------------------------------------------
@@ -66,6 +87,8 @@ __global__ void region_minmax_kernel(const int32_t* __restrict__ xyz, uint64_t n
 	}
 	if ((threadIdx.x & 31) == 0) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
 }
+
+__global__ void set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
 
 // ---- 2. keys ---------------------------------------------------------------------------------------------------
 __global__ void make_keys_kernel(const int32_t* __restrict__ xyz, const uint32_t* __restrict__ rgb, uint64_t n, uint64_t dstOffset,
@@ -350,9 +373,25 @@ void vrm_free_structure(vrm_scene* s)
 	s->storage = -1; s->bytes = 0; s->filled = 0; s->unique = 0;
 }
 
+// VRM_BUILD_TRACE=1: host-clock stage marks on stderr (each mark synchronises the stream, so traced builds are slower)
+struct BuildTrace
+{
+	bool on = getenv("VRM_BUILD_TRACE") != nullptr;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void mark(cudaStream_t st, const char* what)
+	{
+		if (!on) return;
+		cudaStreamSynchronize(st);
+		auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[vrm build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
+
 int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 {
 	cudaStream_t st = s->stream;
+	BuildTrace trace;
 	const uint64_t n = s->nStaged;
 	if (n >= (1ull << 32) - (uint64_t)kSortTile) { s->lastError = "too many voxels for 32-bit indices"; return VRM_ERR_INVALID; }
 	VRM_CUDA(s, cudaEventRecord(s->ev0, st));
@@ -366,6 +405,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 	int hostMinMax[2] = {0, 0};
 	VRM_CUDA(s, cudaMemcpyAsync(hostMinMax, minmax.p, sizeof(hostMinMax), cudaMemcpyDeviceToHost, st));
 	VRM_CUDA(s, cudaStreamSynchronize(st));
+	trace.mark(st, "extent");
 	const int minCoord = hostMinMax[0];
 	const uint64_t D = (uint64_t)(hostMinMax[1] - hostMinMax[0] + 1);
 	if (D > 1024) { s->lastError = "region table diameter > 1024 (scene spans more than 65536 voxels)"; return VRM_ERR_INVALID; }
@@ -380,66 +420,82 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 
 	uint64_t unique = 0;
 	uint32_t numRegions = 0;
-	DeviceBuf ukeys, uvals, regionOf, regionStart;
+	Arena arena;
+	DeviceBuf uvalsBuf, regionStart;
+	unsigned long long* ukeys = nullptr;
+	uint32_t* uvals = nullptr;
+	uint32_t* regionOf = nullptr;
 	if (n > 0)
 	{
 		// 2. keys
-		DeviceBuf keysA, keysB, valsA, valsB, hist, scratch;
 		const uint32_t numTiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
 		const uint64_t histElems = 256ull * numTiles;
-		if (keysA.alloc(n * 8) != cudaSuccess || keysB.alloc(n * 8) != cudaSuccess || valsA.alloc(n * 4) != cudaSuccess || valsB.alloc(n * 4) != cudaSuccess ||
-		    hist.alloc(histElems * 4) != cudaSuccess || scratch.alloc(scan_scratch_elems(std::max<uint64_t>(histElems, n)) * 4) != cudaSuccess)
-		{ cudaGetLastError(); s->lastError = "sort buffer allocation failed"; return VRM_ERR_NOMEM; }
+		const size_t scratchElems = scan_scratch_elems(std::max<uint64_t>(histElems, n));
+		const size_t arenaBytes = 2 * Arena::pad(n * 8) + 2 * Arena::pad(n * 4) + Arena::pad(histElems * 4) + Arena::pad(scratchElems * 4) +
+		                          Arena::pad(n * 4) /* pos */ + Arena::pad(n * 8) /* unique keys */ + Arena::pad(n * 4) /* regionOf */;
+		if (arena.reserve(arenaBytes) != cudaSuccess) { cudaGetLastError(); s->lastError = "build scratch allocation failed"; return VRM_ERR_NOMEM; }
+		trace.mark(st, "arena + region table alloc");
+		unsigned long long* keysA = arena.take<unsigned long long>(n);
+		unsigned long long* keysB = arena.take<unsigned long long>(n);
+		uint32_t* valsA = arena.take<uint32_t>(n);
+		uint32_t* valsB = arena.take<uint32_t>(n);
+		uint32_t* hist = arena.take<uint32_t>(histElems);
+		uint32_t* scratch = arena.take<uint32_t>(scratchElems);
+		uint32_t* pos = arena.take<uint32_t>(n);
+		ukeys = arena.take<unsigned long long>(n);
+		regionOf = arena.take<uint32_t>(n);
+		if (!regionOf) { s->lastError = "build scratch arena too small"; return VRM_ERR_NOMEM; }
 		uint64_t off = 0;
 		for (const VoxelChunk& c : s->chunks)
 		{
 			if (!c.n) continue;
-			make_keys_kernel<<<grid_for(c.n), kThreads, 0, st>>>(c.d_xyz, c.d_rgb, c.n, off, minCoord, (uint32_t)D, keysA.as<unsigned long long>(), valsA.as<uint32_t>());
+			make_keys_kernel<<<grid_for(c.n), kThreads, 0, st>>>(c.d_xyz, c.d_rgb, c.n, off, minCoord, (uint32_t)D, keysA, valsA);
 			off += c.n;
 		}
+		trace.mark(st, "keys");
 		// 3. stable LSD radix sort
-		unsigned long long* kin = keysA.as<unsigned long long>(); unsigned long long* kout = keysB.as<unsigned long long>();
-		uint32_t* vin = valsA.as<uint32_t>(); uint32_t* vout = valsB.as<uint32_t>();
+		unsigned long long* kin = keysA; unsigned long long* kout = keysB;
+		uint32_t* vin = valsA; uint32_t* vout = valsB;
 		for (int shift = 0; shift < keyBits; shift += 8)
 		{
-			radix_hist_kernel<<<numTiles, kThreads, 0, st>>>(kin, n, shift, numTiles, hist.as<uint32_t>());
-			exclusive_scan(hist.as<uint32_t>(), hist.as<uint32_t>(), histElems, scratch.as<uint32_t>(), st);
-			radix_scatter_kernel<<<numTiles, kThreads, 0, st>>>(kin, vin, n, shift, numTiles, hist.as<uint32_t>(), kout, vout);
+			radix_hist_kernel<<<numTiles, kThreads, 0, st>>>(kin, n, shift, numTiles, hist);
+			exclusive_scan(hist, hist, histElems, scratch, st);
+			radix_scatter_kernel<<<numTiles, kThreads, 0, st>>>(kin, vin, n, shift, numTiles, hist, kout, vout);
 			std::swap(kin, kout); std::swap(vin, vout);
 		}
-		// 4. dedupe (kout / vout are free now: reuse vout as the keep flags, hist is too small -> allocate pos)
-		DeviceBuf pos;
-		if (pos.alloc(n * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "dedupe buffer allocation failed"; return VRM_ERR_NOMEM; }
+		trace.mark(st, "radix sort");
+		// 4. dedupe (kout / vout are free now: vout holds the keep flags)
 		uint32_t* keep = vout;
 		keep_last_kernel<<<grid_for(n), kThreads, 0, st>>>(kin, n, keep);
-		exclusive_scan(keep, pos.as<uint32_t>(), n, scratch.as<uint32_t>(), st);
+		exclusive_scan(keep, pos, n, scratch, st);
 		uint32_t lastPos = 0, lastKeep = 0;
-		VRM_CUDA(s, cudaMemcpyAsync(&lastPos, pos.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+		VRM_CUDA(s, cudaMemcpyAsync(&lastPos, pos + (n - 1), 4, cudaMemcpyDeviceToHost, st));
 		VRM_CUDA(s, cudaMemcpyAsync(&lastKeep, keep + (n - 1), 4, cudaMemcpyDeviceToHost, st));
 		VRM_CUDA(s, cudaStreamSynchronize(st));
 		unique = (uint64_t)lastPos + lastKeep;
-		if (ukeys.alloc(unique * 8) != cudaSuccess || uvals.alloc(unique * 4) != cudaSuccess || regionOf.alloc(unique * 4) != cudaSuccess)
-		{ cudaGetLastError(); s->lastError = "unique voxel allocation failed"; return VRM_ERR_NOMEM; }
-		compact_kernel<<<grid_for(n), kThreads, 0, st>>>(kin, vin, keep, pos.as<uint32_t>(), n, ukeys.as<unsigned long long>(), uvals.as<uint32_t>());
+		// the colours outlive the build (VCS: the values array), so they get their own, exactly sized allocation
+		if (uvalsBuf.alloc(unique * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "unique voxel allocation failed"; return VRM_ERR_NOMEM; }
+		uvals = uvalsBuf.as<uint32_t>();
+		compact_kernel<<<grid_for(n), kThreads, 0, st>>>(kin, vin, keep, pos, n, ukeys, uvals);
+		trace.mark(st, "dedupe + compact");
 		// 5. region directory (reuse pos / keep as head-scan / head flags: unique <= n)
 		uint32_t* head = keep;
-		uint32_t* headScan = pos.as<uint32_t>();
-		region_head_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), unique, head);
-		exclusive_scan(head, headScan, unique, scratch.as<uint32_t>(), st);
+		uint32_t* headScan = pos;
+		region_head_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, unique, head);
+		exclusive_scan(head, headScan, unique, scratch, st);
 		uint32_t lastScan = 0, lastHead = 0;
 		VRM_CUDA(s, cudaMemcpyAsync(&lastScan, headScan + (unique - 1), 4, cudaMemcpyDeviceToHost, st));
 		VRM_CUDA(s, cudaMemcpyAsync(&lastHead, head + (unique - 1), 4, cudaMemcpyDeviceToHost, st));
 		VRM_CUDA(s, cudaStreamSynchronize(st));
 		numRegions = lastScan + lastHead;
 		if (regionStart.alloc(((size_t)numRegions + 1) * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "region directory allocation failed"; return VRM_ERR_NOMEM; }
-		region_dir_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), head, headScan, unique, regionTable.as<int32_t>(),
-		                                                          regionStart.as<uint32_t>(), regionOf.as<uint32_t>());
-		uint32_t u32 = (uint32_t)unique;
-		VRM_CUDA(s, cudaMemcpyAsync(regionStart.as<uint32_t>() + numRegions, &u32, 4, cudaMemcpyHostToDevice, st));
-		VRM_CUDA(s, cudaStreamSynchronize(st));  // keep/pos/scratch (and &u32) go out of scope below
+		region_dir_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, head, headScan, unique, regionTable.as<int32_t>(), regionStart.as<uint32_t>(), regionOf);
+		// regionStart[numRegions] = unique, written from the device (no host staging variable to keep alive)
+		set_u32_kernel<<<1, 1, 0, st>>>(regionStart.as<uint32_t>() + numRegions, (uint32_t)unique);
 		VRM_CUDA(s, cudaGetLastError());
 	}
 
+	trace.mark(st, "region directory");
 	uint64_t bytes = tableSize * sizeof(int32_t);
 	DeviceBuf headers, clusterMask, hashDesc, slots;
 	if (storageType == VRM_STORAGE_VCS)
@@ -452,7 +508,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 		VRM_CUDA(s, cudaMemsetAsync(headers.p, 0, headerBytes, st));
 		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4, st));
 		if (unique)
-			vcs_fill_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), regionOf.as<uint32_t>(), unique, headers.as<uint2>(), clusterMask.as<uint32_t>());
+			vcs_fill_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, regionOf, unique, headers.as<uint2>(), clusterMask.as<uint32_t>());
 		if (unique)
 			vcs_flag_clusters_kernel<<<grid_for((uint64_t)numRegions * 512), kThreads, 0, st>>>(headers.as<uint2>(), clusterMask.as<uint32_t>(), (uint64_t)numRegions * 512);
 		VRM_CUDA(s, cudaGetLastError());
@@ -488,13 +544,14 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 			for (;; attempt++)
 			{
 				VRM_CUDA(s, cudaMemsetAsync(failed.p, 0, (size_t)numRegions * 4, st));
-				cuckoo_insert_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys.as<unsigned long long>(), uvals.as<uint32_t>(), regionOf.as<uint32_t>(), unique,
+				cuckoo_insert_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, uvals, regionOf, unique,
 				                                                           hashDesc.as<HashRegionDesc>(), slots.as<unsigned long long>(), all ? nullptr : retry.as<uint32_t>(), failed.as<uint32_t>());
 				VRM_CUDA(s, cudaMemcpyAsync(hostFailed.data(), failed.p, (size_t)numRegions * 4, cudaMemcpyDeviceToHost, st));
 				VRM_CUDA(s, cudaStreamSynchronize(st));
 				bool any = false;
 				for (uint32_t r = 0; r < numRegions; r++)
 					if (hostFailed[r]) { any = true; desc[r].seed1 = seed_for(r, attempt + 1, 1); desc[r].seed2 = seed_for(r, attempt + 1, 2); }
+				if (trace.on) { uint32_t nf = 0; for (uint32_t r = 0; r < numRegions; r++) nf += hostFailed[r] ? 1u : 0u; fprintf(stderr, "[vrm build] cuckoo attempt %d: %u regions failed\n", attempt, nf); }
 				if (!any) break;
 				if (attempt + 1 >= kMaxRebuilds) { s->lastError = "cuckoo insertion did not converge"; return VRM_ERR_BUILD; }
 				VRM_CUDA(s, cudaMemcpyAsync(hashDesc.p, desc.data(), desc.size() * sizeof(HashRegionDesc), cudaMemcpyHostToDevice, st));
@@ -506,6 +563,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 		}
 		bytes += (size_t)numRegions * sizeof(HashRegionDesc) + totalSlots * 8;
 	}
+	trace.mark(st, storageType == VRM_STORAGE_VCS ? "vcs tables" : "cuckoo insertion");
 	VRM_CUDA(s, cudaEventRecord(s->ev1, st));
 	VRM_CUDA(s, cudaStreamSynchronize(st));
 	VRM_CUDA(s, cudaGetLastError());
@@ -516,7 +574,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 	{
 		s->d_headers = static_cast<uint2*>(headers.release());
 		s->d_clusterMask = static_cast<uint32_t*>(clusterMask.release());
-		s->d_values = static_cast<uint32_t*>(uvals.release());
+		s->d_values = static_cast<uint32_t*>(uvalsBuf.release());
 	}
 	else
 	{
@@ -531,3 +589,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 	s->bytes = bytes;
 	return VRM_OK;
 }
+
+// exclusive scan for the other translation units (vrm_generate.cu)
+size_t vrm_scan_scratch_elems(uint64_t n) { return scan_scratch_elems(n); }
+void vrm_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st) { exclusive_scan(in, out, n, scratch, st); }

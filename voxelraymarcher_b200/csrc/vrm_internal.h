@@ -79,6 +79,8 @@ int vrm_fail_cuda(vrm_scene* s, cudaError_t e, const char* what);
 // vrm_build.cu
 int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs);
 void vrm_free_structure(vrm_scene* s);
+size_t vrm_scan_scratch_elems(uint64_t n);  // uint32 elements of scratch an exclusive scan of n elements needs
+void vrm_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st);  // out may alias in
 
 // vrm_render.cu
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
