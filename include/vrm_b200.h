@@ -125,6 +125,15 @@ int vrm_render_views_device(vrm_scene* scene, const float* cameras, uint32_t n_v
                             uint32_t scale, int algorithm, uint32_t width, uint32_t height, uint8_t* d_rgb_out,
                             int32_t* d_hits_out);
 
+/* Streaming multi-view render into HOST frames (n_views x height x width x 3, view-major): the camera orbit of
+ * BASELINE.json configs[3] as one call (the reference renders exactly one frame per process, main/Main.cu:105-163).
+ * Pinned (cudaHostAlloc / cudaHostRegister'ed) rgb_out: the kernel stores every view straight into it.  Pageable
+ * rgb_out: views are rendered in batches into two device buffers in turn and the copy of a finished batch overlaps the
+ * rendering of the next (batch size: VRM_VIEW_BATCH_BYTES, default 256 MiB).  total_ms (nullable): device time from the
+ * first launch to the last byte on the host. */
+int vrm_render_views(vrm_scene* scene, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale,
+                     int algorithm, uint32_t width, uint32_t height, uint8_t* rgb_out, float* total_ms);
+
 /* Arbitrary world rays: rays = n x 6 floats (origin xyz, direction xyz).  colour_out = n x uint32, the value the
  * reference's rayMarchVoxelScene[LongestAxis] returns (0 = background); hits_out nullable as above. */
 int vrm_trace_rays(vrm_scene* scene, const float* rays, uint64_t n, const float translation[3], uint32_t scale,
@@ -149,6 +158,11 @@ int vrm_copy_device(int device, void* d_dst, const void* d_src, uint64_t bytes);
 /* The storage seam on GLOBAL voxel coordinates: out[i] = colour or VRM_EMPTY; exists_out[i] (nullable) =
  * doesVoxelSpaceExist (always 1 inside a non-empty region for the hash table; cluster occupancy for the VCS). */
 int vrm_lookup(vrm_scene* scene, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* exists_out);
+
+/* Opt-in L2 residency hint: an access-policy window (persisting) over the structure's hottest array -- the VCS cluster
+ * headers or the hash table's slots -- on the handle's current stream (also VRM_L2_PERSIST=1 at vrm_scene_create).  Off by
+ * default: on the BASELINE scenes the touched working set already lives in L1/L2 and the window measured no gain. */
+int vrm_set_l2_persistence(vrm_scene* scene, int enabled);
 
 /* Event counters of the LAST render / trace call made with statistics enabled (vrm_set_statistics(scene, 1)):
  * out[0] exist checks, [1] exist checks answering false, [2] lookups, [3] lookups that found a voxel,

@@ -14,7 +14,7 @@ from voxelraymarcher_b200 import api
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "vrm_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(vrm_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(vrm_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -326,3 +326,29 @@ def test_gpu_scene_generators_match_host_generators(kind, kw, storage):
         assert int(ra["hits"][..., 3].sum()) > 1000
     host.close()
     dev.close()
+
+
+def test_streaming_multi_view_render_equals_single_renders(probe, monkeypatch):
+    """vrm_render_views (camera orbit into host frames): pageable frames go through double-buffered device batches (forced to
+    2 views per batch here, so 7 views = 4 batches exercise the buffer hand-over), pinned frames are written directly; both must
+    equal the single-frame renders bit for bit."""
+    import torch
+    xyz, rgb = probe
+    w, h = 256, 144
+    monkeypatch.setenv("VRM_VIEW_BATCH_BYTES", str(2 * w * h * 3))
+    s = api.VoxelScene(0)
+    s.add_voxels(xyz, rgb)
+    s.generate_voxel_scene("vcs")
+    cams = []
+    for v in range(7):
+        ang = 2.0 * np.pi * (v + 0.31) / 7
+        cams.append(api.Camera((6.0 + 9.0 * np.cos(ang), 3.0 + 0.3 * v, 6.0 + 9.0 * np.sin(ang)), (6.0, 2.0, 2.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h)))
+    for algo in ("longestaxis", "original"):
+        singles = np.stack([s.render(w, h, algo, c, scale=8)["rgb"] for c in cams])
+        assert singles.any()
+        pageable = s.render_views(w, h, algo, cams, scale=8)
+        assert np.array_equal(pageable["rgb"], singles)
+        pinned = torch.zeros((7, h, w, 3), dtype=torch.uint8).pin_memory()
+        got = s.render_views(w, h, algo, cams, scale=8, rgb_out=pinned.numpy())
+        assert np.array_equal(got["rgb"], singles)
+    s.close()

@@ -33,8 +33,8 @@ EXPORTS = [
     "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
     "vrm_scene_generate_terrain", "vrm_scene_generate_sparse_shells",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
-    "vrm_render_device", "vrm_render_views_device", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
-    "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
+    "vrm_render_device", "vrm_render_views_device", "vrm_render_views", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
+    "vrm_set_l2_persistence", "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library():
         "vrm_render": (ci, [vp, vp, vp, u32, ci, u32, u32, vp, vp, C.POINTER(f32)]),
         "vrm_render_device": (ci, [vp, vp, vp, u32, ci, u32, u32, vp, vp]),
         "vrm_render_views_device": (ci, [vp, vp, u32, vp, u32, ci, u32, u32, vp, vp]),
+        "vrm_render_views": (ci, [vp, vp, u32, vp, u32, ci, u32, u32, vp, C.POINTER(f32)]),
         "vrm_trace_rays": (ci, [vp, vp, u64, vp, u32, ci, vp, vp, C.POINTER(f32)]),
         "vrm_trace_rays_device": (ci, [vp, vp, u64, vp, u32, ci, vp, vp]),
         "vrm_lookup": (ci, [vp, vp, u64, vp, vp]),
@@ -86,6 +87,7 @@ def load_library():
         "vrm_peer_close": (ci, [ci, vp]),
         "vrm_peer_free": (ci, [ci, vp]),
         "vrm_copy_device": (ci, [ci, vp, vp, u64]),
+        "vrm_set_l2_persistence": (ci, [vp, ci]),
         "vrm_set_statistics": (ci, [vp, ci]),
         "vrm_get_statistics": (ci, [vp, vp]),
     }
@@ -269,6 +271,19 @@ class VoxelScene:
         self._check(self.lib.vrm_render_views_device(self.h, _ptr(cams), cams.shape[0], _ptr(_f3(translation)), scale, self._algo(algorithm),
                                                      width, height, C.c_void_p(d_rgb_ptr), C.c_void_p(d_hits_ptr or 0)), "vrm_render_views_device")
 
+    def render_views(self, width, height, algorithm, cameras, scale=1, translation=(0.0, 0.0, 0.0), rgb_out=None):
+        """A batch of views (camera orbit) into host frames ``[n, H, W, 3]``; ``rgb_out`` may be a pinned buffer (written directly
+        by the kernel) or pageable memory (double-buffered device batches, copies overlapped with rendering)."""
+        cams = np.ascontiguousarray(np.stack([self._cam(c) for c in cameras]).astype(np.float32))
+        n = cams.shape[0]
+        if rgb_out is None:
+            rgb_out = np.zeros((n, height, width, 3), np.uint8)
+        assert rgb_out.dtype == np.uint8 and rgb_out.size == n * height * width * 3 and rgb_out.flags["C_CONTIGUOUS"]
+        ms = C.c_float()
+        self._check(self.lib.vrm_render_views(self.h, _ptr(cams), n, _ptr(_f3(translation)), int(scale), self._algo(algorithm), width, height,
+                                              _ptr(rgb_out), C.byref(ms)), "vrm_render_views")
+        return {"rgb": rgb_out.reshape(n, height, width, 3), "total_ms": ms.value}
+
     def trace_rays(self, rays, algorithm, scale=1, translation=(0.0, 0.0, 0.0), want_hits=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         n = rays.shape[0]
@@ -293,6 +308,9 @@ class VoxelScene:
         return out, exists
 
     # -- statistics ----------------------------------------------------------------------------------------------
+    def set_l2_persistence(self, enabled: bool):
+        self._check(self.lib.vrm_set_l2_persistence(self.h, int(enabled)), "vrm_set_l2_persistence")
+
     def set_statistics(self, enabled: bool):
         self._check(self.lib.vrm_set_statistics(self.h, int(enabled)), "vrm_set_statistics")
 

@@ -16,6 +16,51 @@ int vrm_fail_cuda(vrm_scene* s, cudaError_t e, const char* what)
 	return e == cudaErrorMemoryAllocation ? VRM_ERR_NOMEM : VRM_ERR_CUDA;
 }
 
+// The structure's hottest array gets an L2 access-policy window on the launching stream: VCS -> the cluster headers
+// (64 KB per region), hash table -> the slot array (hit ratio scaled to the persisting carve-out when it is larger).
+void vrm_apply_l2_window(vrm_scene* s)
+{
+	const bool want = s->l2Persist && s->storage >= 0;
+	if (want == s->l2WindowOn && (!want || s->l2WindowStream == s->stream)) return;
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof(attr));
+	if (s->l2WindowOn && s->l2WindowStream && s->l2WindowStream != s->stream)
+	{
+		attr.accessPolicyWindow.num_bytes = 0;  // remove the window from the stream it was on
+		cudaStreamSetAttribute(s->l2WindowStream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	}
+	if (want)
+	{
+		int maxPersist = 0, maxWindow = 0;
+		cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, s->device);
+		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
+		void* base = s->storage == VRM_STORAGE_VCS ? static_cast<void*>(s->d_headers) : static_cast<void*>(s->d_slots);
+		size_t bytes = s->storage == VRM_STORAGE_VCS ? (size_t)s->filled * 512 * 16 * sizeof(uint2) : 0;
+		if (s->storage == VRM_STORAGE_HASHTABLE) bytes = s->bytes - (size_t)s->filled * sizeof(vrm::HashRegionDesc) - (size_t)s->diameter * s->diameter * s->diameter * 4;
+		if (base && bytes && maxPersist > 0 && maxWindow > 0)
+		{
+			const size_t carve = (size_t)maxPersist * 3 / 4;
+			cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+			const size_t window = bytes < (size_t)maxWindow ? bytes : (size_t)maxWindow;
+			attr.accessPolicyWindow.base_ptr = base;
+			attr.accessPolicyWindow.num_bytes = window;
+			attr.accessPolicyWindow.hitRatio = window <= carve ? 1.0f : (float)((double)carve / (double)window);
+			attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+		}
+	}
+	else
+	{
+		attr.accessPolicyWindow.num_bytes = 0;
+		cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+		cudaCtxResetPersistingL2Cache();
+	}
+	cudaGetLastError();
+	s->l2WindowOn = want;
+	s->l2WindowStream = want ? s->stream : nullptr;
+}
+
 namespace
 {
 
@@ -133,6 +178,8 @@ int vrm_scene_create(int device, vrm_scene** out)
 
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->numSms, cudaDevAttrMultiProcessorCount, device);
 	if (const char* mode = getenv("VRM_RENDER_MODE")) s->renderMode = atoi(mode);
+	if (const char* lp = getenv("VRM_L2_PERSIST")) s->l2Persist = atoi(lp) != 0;
+	if (const char* bb = getenv("VRM_VIEW_BATCH_BYTES")) { long long v = atoll(bb); if (v > 0) s->viewBatchBytes = (size_t)v; }
 	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }
 	s->stream = s->ownStream;
 	cudaEventRecord(s->ev1, s->stream);
@@ -152,6 +199,13 @@ int vrm_scene_destroy(vrm_scene* s)
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);
 	if (s->ownStream) cudaStreamDestroy(s->ownStream);
+	if (s->copyStream) cudaStreamDestroy(s->copyStream);
+	for (int i = 0; i < 2; i++)
+	{
+		if (s->evRendered[i]) cudaEventDestroy(s->evRendered[i]);
+		if (s->evCopied[i]) cudaEventDestroy(s->evCopied[i]);
+		cudaFree(s->d_batch[i]);
+	}
 
 	cudaGetLastError();
 	delete s;
@@ -296,6 +350,86 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 	return VRM_OK;
 }
 
+int vrm_render_views(vrm_scene* s, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale, int algorithm,
+                     uint32_t width, uint32_t height, uint8_t* rgb_out, float* total_ms)
+{
+	int rc = check_render_args(s, cameras, translation, algorithm, width, height);
+	if (rc) return rc;
+	if (!rgb_out || n_views == 0) { s->lastError = "invalid render arguments"; return VRM_ERR_INVALID; }
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	const size_t frameBytes = (size_t)width * height * 3;
+	cudaPointerAttributes at;
+	uint8_t* mapped = nullptr;
+	if (cudaPointerGetAttributes(&at, rgb_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) mapped = static_cast<uint8_t*>(at.devicePointer);
+	cudaGetLastError();
+	const uint32_t maxViewsPerLaunch = 65535;
+	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
+	if (mapped)
+	{
+		// pinned frames: every view is stored straight into the caller's memory by the kernel (as in vrm_render)
+		for (uint32_t v0 = 0; v0 < n_views; v0 += maxViewsPerLaunch)
+		{
+			const uint32_t nv = n_views - v0 < maxViewsPerLaunch ? n_views - v0 : maxViewsPerLaunch;
+			rc = upload_cameras(s, cameras + (size_t)v0 * VRM_CAMERA_FLOATS, nv);
+			if (rc) return rc;
+			rc = vrm_launch_render(s, s->d_cams, nv, translation, scale, algorithm, width, height, mapped + (size_t)v0 * frameBytes, nullptr);
+			if (rc) return rc;
+		}
+		VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+		VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	}
+	else
+	{
+		// pageable frames: batches of views rendered into two device buffers in turn; the device-to-host copy of batch k runs on a
+		// second stream while batch k+1 renders
+		size_t perBatch = s->viewBatchBytes / frameBytes;
+		if (perBatch < 1) perBatch = 1;
+		if (perBatch > n_views) perBatch = n_views;
+		if (perBatch > maxViewsPerLaunch) perBatch = maxViewsPerLaunch;
+		const size_t need = perBatch * frameBytes;
+		if (!s->copyStream)
+		{
+			VRM_CUDA(s, cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+			for (int i = 0; i < 2; i++)
+			{
+				VRM_CUDA(s, cudaEventCreateWithFlags(&s->evRendered[i], cudaEventDisableTiming));
+				VRM_CUDA(s, cudaEventCreateWithFlags(&s->evCopied[i], cudaEventDisableTiming));
+			}
+		}
+		if (s->batchBytes < need)
+		{
+			VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+			VRM_CUDA(s, cudaStreamSynchronize(s->copyStream));
+			for (int i = 0; i < 2; i++) { cudaFree(s->d_batch[i]); s->d_batch[i] = nullptr; }
+			s->batchBytes = 0;
+			for (int i = 0; i < 2; i++) VRM_CUDA(s, cudaMalloc(&s->d_batch[i], need));
+			s->batchBytes = need;
+		}
+		uint32_t batch = 0;
+		for (uint32_t v0 = 0; v0 < n_views; v0 += (uint32_t)perBatch, batch++)
+		{
+			const int slot = (int)(batch & 1u);
+			const uint32_t nv = n_views - v0 < perBatch ? n_views - v0 : (uint32_t)perBatch;
+			if (batch >= 2) VRM_CUDA(s, cudaStreamWaitEvent(s->stream, s->evCopied[slot], 0));  // the buffer's previous batch has left the device
+			rc = upload_cameras(s, cameras + (size_t)v0 * VRM_CAMERA_FLOATS, nv);
+			if (rc) return rc;
+			rc = vrm_launch_render(s, s->d_cams, nv, translation, scale, algorithm, width, height, s->d_batch[slot], nullptr);
+			if (rc) return rc;
+			VRM_CUDA(s, cudaEventRecord(s->evRendered[slot], s->stream));
+			VRM_CUDA(s, cudaStreamWaitEvent(s->copyStream, s->evRendered[slot], 0));
+			VRM_CUDA(s, cudaMemcpyAsync(rgb_out + (size_t)v0 * frameBytes, s->d_batch[slot], (size_t)nv * frameBytes, cudaMemcpyDeviceToHost, s->copyStream));
+			VRM_CUDA(s, cudaEventRecord(s->evCopied[slot], s->copyStream));
+		}
+		VRM_CUDA(s, cudaStreamWaitEvent(s->stream, s->evCopied[(batch - 1) & 1u], 0));
+		if (batch >= 2) VRM_CUDA(s, cudaStreamWaitEvent(s->stream, s->evCopied[batch & 1u], 0));
+		VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
+		VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+		VRM_CUDA(s, cudaStreamSynchronize(s->copyStream));
+	}
+	if (total_ms) VRM_CUDA(s, cudaEventElapsedTime(total_ms, s->ev0, s->ev1));
+	return VRM_OK;
+}
+
 int vrm_trace_rays_device(vrm_scene* s, const float* d_rays, uint64_t n, const float translation[3], uint32_t scale, int algorithm,
                           uint32_t* d_colour_out, int32_t* d_hits_out)
 {
@@ -404,6 +538,15 @@ int vrm_copy_device(int device, void* d_dst, const void* d_src, uint64_t bytes)
 {
 	if (!d_dst || !d_src) return VRM_ERR_INVALID;
 	if (cudaSetDevice(device) != cudaSuccess || cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaGetLastError(); return VRM_ERR_CUDA; }
+	return VRM_OK;
+}
+
+int vrm_set_l2_persistence(vrm_scene* s, int enabled)
+{
+	if (!s) return VRM_ERR_INVALID;
+	VRM_CUDA(s, cudaSetDevice(s->device));
+	s->l2Persist = enabled != 0;
+	vrm_apply_l2_window(s);
 	return VRM_OK;
 }
 

@@ -49,10 +49,21 @@ struct vrm_scene
 	float* h_cams = nullptr;     // pinned staging for cameras
 	void* d_io = nullptr;        size_t ioBytes = 0;   // rays / lookup queries and results
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// streaming multi-view renders into pageable host memory (vrm_render_views): double-buffered device batches
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t evRendered[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
+	uint8_t* d_batch[2] = {nullptr, nullptr};  size_t batchBytes = 0;
+	size_t viewBatchBytes = size_t(256) << 20;  // device bytes per batch buffer (VRM_VIEW_BATCH_BYTES)
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
 	int numSms = 148;
 	int renderMode = -1;              // -1 = per-combination default (vrm_render.cu); 0 = scheduled persistent kernel, 1 = nested loops, 2 = per-lane state machine (VRM_RENDER_MODE)
+
+	// L2 access-policy window over the structure's hottest array (vrm_set_l2_persistence / VRM_L2_PERSIST=1; off by default:
+	// measured no gain on the BASELINE scenes, whose touched working set already lives in L1/L2 -- DESIGN.md 3.2)
+	bool l2Persist = false;
+	cudaStream_t l2WindowStream = nullptr;  // stream the window is currently installed on
+	bool l2WindowOn = false;
 
 	bool statsEnabled = false;
 	vrm::Stats* d_stats = nullptr;
@@ -81,6 +92,9 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs);
 void vrm_free_structure(vrm_scene* s);
 size_t vrm_scan_scratch_elems(uint64_t n);  // uint32 elements of scratch an exclusive scan of n elements needs
 void vrm_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st);  // out may alias in
+
+// vrm_api.cu: install / remove the access-policy window on the handle's current stream (called by the launch wrappers)
+void vrm_apply_l2_window(vrm_scene* s);
 
 // vrm_render.cu
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,

@@ -397,6 +397,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
                       uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase, uint32_t yEnd)
 {
 	if (yEnd > H) yEnd = H;
+	vrm_apply_l2_window(s);
 	RenderArgs a;
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
@@ -427,6 +428,7 @@ int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float*
                      uint32_t* d_colour, int32_t* d_hits)
 {
 	if (n == 0) return VRM_OK;
+	vrm_apply_l2_window(s);
 	TraceArgs a;
 	fill_common(a, s, translation, scale);
 	a.rays = d_rays; a.n = n; a.colour = d_colour; a.hits = d_hits;
