@@ -24,10 +24,10 @@
 
 #if defined(__CUDACC__)
 #define VRM_HD __host__ __device__ __forceinline__
-#define VRM_HD_NOINLINE __host__ __device__ __noinline__
+#define VRM_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define VRM_HD inline
-#define VRM_HD_NOINLINE
+#define VRM_HD_NOINLINE static inline
 #endif
 
 namespace vrm
@@ -134,13 +134,24 @@ VRM_HD void div3(float x0, float x1, float x2, const RayDir& k, float& a0, float
 	}
 }
 
+// VRM_COLD_OUTLINE=1 keeps IEEE division (and the crawl fast-forward) OUT of line: the slow branches below run for a handful of rays per frame, and three inlined div.rn
+// expansions per site sit in the middle of the hot loop instruction stream.  Measured: no difference (1.588 vs 1.582 ms), so inline stays the default
+#ifndef VRM_COLD_OUTLINE
+#define VRM_COLD_OUTLINE 0
+#endif
+#if VRM_COLD_OUTLINE
+VRM_HD_NOINLINE float vdiv_cold(float a, float b) { return vdiv(a, b); }
+#else
+VRM_HD float vdiv_cold(float a, float b) { return vdiv(a, b); }
+#endif
+
 // the same with the constants passed one by one (vrm_flat.cuh keeps them in individual registers)
 VRM_HD void div3(float x0, float x1, float x2, float d0, float d1, float d2, float r0, float r1, float r2, float thr, float& a0, float& a1, float& a2)
 {
 	float m = fminf(fabsf(x0), fminf(fabsf(x1), fabsf(x2)));
 	if (!(m >= thr))
 	{
-		a0 = vdiv(x0, d0); a1 = vdiv(x1, d1); a2 = vdiv(x2, d2);
+		a0 = vdiv_cold(x0, d0); a1 = vdiv_cold(x1, d1); a2 = vdiv_cold(x2, d2);
 	}
 	else
 	{
@@ -150,7 +161,7 @@ VRM_HD void div3(float x0, float x1, float x2, float d0, float d1, float d2, flo
 
 VRM_HD float div1(float x, float d, float rd, float thr)
 {
-	if (!(fabsf(x) >= thr)) return vdiv(x, d);
+	if (!(fabsf(x) >= thr)) return vdiv_cold(x, d);
 	return div_by_const(x, d, rd);
 }
 
@@ -602,6 +613,24 @@ VRM_HD int crawl_skip(float* o, const float* dir, float thr, int v0, int v1, int
 }
 
 VRM_HD int crawl_skip(float* o, const RayDir& k, int v0, int v1, int v2) { return crawl_skip(o, k.d, k.thr, v0, v1, v2); }
+
+// Out-of-line form for the state machine: position and direction travel by value / through a small struct so that the
+// caller's registers are not forced into local memory.
+struct CrawlResult { float o0, o1, o2; int skipped; };
+#if VRM_COLD_OUTLINE
+VRM_HD_NOINLINE
+#else
+VRM_HD
+#endif
+CrawlResult crawl_skip_cold(float o0, float o1, float o2, float d0, float d1, float d2, float thr, int v0, int v1, int v2)
+{
+	float o[3] = {o0, o1, o2};
+	const float d[3] = {d0, d1, d2};
+	CrawlResult r;
+	r.skipped = crawl_skip(o, d, thr, v0, v1, v2);
+	r.o0 = o[0]; r.o1 = o[1]; r.o2 = o[2];
+	return r;
+}
 
 // Renderer.cuh:421-429: move region coordinates by floor(o / 64) and rebase the local position
 VRM_HD void rebase_region(float* o, int* reg)

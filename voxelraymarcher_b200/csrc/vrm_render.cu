@@ -22,6 +22,9 @@ namespace
 #ifndef VRM_BLOCK_TILES_X
 #define VRM_BLOCK_TILES_X 4
 #endif
+#ifndef VRM_HIT_BARRIER
+#define VRM_HIT_BARRIER 1  // VCS + longest axis state machine: 1 = a tile shades and starts its shadow rays together (march_scene_flat_warp), 0 = independent lanes
+#endif
 #ifndef VRM_WARP_STORE
 #define VRM_WARP_STORE 0
 #endif
@@ -29,7 +32,10 @@ namespace
 #define VRM_FLAT_LA_MINBLOCKS 4
 #endif
 
-constexpr int kTileW = 8, kTileH = 4;          // pixels per warp
+#ifndef VRM_TILE_W
+#define VRM_TILE_W 8
+#endif
+constexpr int kTileW = VRM_TILE_W, kTileH = 32 / VRM_TILE_W;          // pixels per warp
 constexpr int kBlockTilesX = VRM_BLOCK_TILES_X, kBlockTilesY = VRM_BLOCK_TILES_Y;
 constexpr int kBlockW = kTileW * kBlockTilesX;  // 32
 constexpr int kBlockH = kTileH * kBlockTilesY;  // 8
@@ -90,7 +96,26 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
 	uint32_t color = 0;
-	if (inside)
+	if constexpr (FLATLOOP && VRM_HIT_BARRIER != 0 && ST == kStorageVcs && ALGO != kAlgoOriginal)
+	{
+		// warp-cooperative state machine: every lane takes part in the votes, lanes outside the image just idle
+		float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
+		if (inside)
+		{
+			const float* cam = a.cams + (size_t)blockIdx.z * 15;
+			float camv[15];
+#pragma unroll
+			for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+			primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
+			if (a.hits)
+			{
+				c.hitOut = a.hits + 4 * (((size_t)blockIdx.z * a.H + y) * a.W + x);
+				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+			}
+		}
+		color = march_scene_flat_warp<ST, ALGO, STATS>(c, inside, o, d, a.scale);
+	}
+	else if (inside)
 	{
 		const float* cam = a.cams + (size_t)blockIdx.z * 15;
 		float camv[15];
