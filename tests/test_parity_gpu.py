@@ -352,3 +352,36 @@ def test_streaming_multi_view_render_equals_single_renders(probe, monkeypatch):
         got = s.render_views(w, h, algo, cams, scale=8, rgb_out=pinned.numpy())
         assert np.array_equal(got["rgb"], singles)
     s.close()
+
+
+@pytest.mark.parametrize("storage,algo", COMBOS)
+@pytest.mark.parametrize("w,h", [(250, 141), (33, 5), (7, 3), (1, 1)])
+def test_ragged_resolutions_match_oracle(probe, storage, algo, w, h):
+    """Image sizes that are not multiples of the 8x4 warp tile / 32x4 CTA (lanes and warps without a pixel take part in the
+    warp-cooperative state machine; rows that are not 4-byte aligned take the per-pixel store path)."""
+    xyz, rgb = probe
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    s = build_product(xyz, rgb, storage)
+    ref = build_oracle(kind, xyz, rgb, storage)
+    cam = camera((6.0, 2.0, 6.0), (0.0, 0.0, -1.0), 60.0, w, h, kind)
+    got = s.render(w, h, algo, cam, scale=8, want_hits=True)
+    want = ref.render(cam, w, h, algo, scale=8)
+    assert np.array_equal(got["hits"], want["hits"])
+    assert np.array_equal(got["rgb"], want["rgb"])
+    s.close()
+
+
+def test_scene_generator_argument_errors():
+    s = api.VoxelScene(0)
+    for bad in (dict(size=1), dict(size=5000)):
+        with pytest.raises(api.VrmError):
+            s.generate_terrain(bad["size"], 1)
+    for size, cell in ((100, 64), (64, 4), (1024, 512)):
+        with pytest.raises(api.VrmError):
+            s.generate_sparse_shells(size, cell, 7, 35)
+    assert s.generate_sparse_shells(128, 64, 7, 0) == 0          # nothing kept: an empty but valid scene
+    s.generate_voxel_scene("vcs")
+    with pytest.raises(api.VrmError):
+        s.generate_terrain(64, 1)                                 # already built
+    s.close()

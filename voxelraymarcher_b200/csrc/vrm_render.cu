@@ -25,6 +25,9 @@ namespace
 #ifndef VRM_HIT_BARRIER
 #define VRM_HIT_BARRIER 1  // VCS + longest axis state machine: 1 = a tile shades and starts its shadow rays together (march_scene_flat_warp), 0 = independent lanes
 #endif
+#ifndef VRM_TRACE_HIT_BARRIER
+#define VRM_TRACE_HIT_BARRIER 0  // the same for trace_rays (arbitrary rays)
+#endif
 #ifndef VRM_WARP_STORE
 #define VRM_WARP_STORE 0
 #endif
@@ -307,7 +310,24 @@ __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 	c.hitOut = nullptr;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
-	if (i < a.n)
+	if constexpr (FLATLOOP && VRM_TRACE_HIT_BARRIER != 0 && ST == kStorageVcs && ALGO != kAlgoOriginal)
+	{
+		// warp-cooperative state machine with the hit barrier (see render_kernel); lanes past the end of the ray list idle
+		const bool active = i < a.n;
+		float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
+		if (active)
+		{
+			for (int k = 0; k < 3; k++) { o[k] = __ldg(a.rays + 6 * i + k); d[k] = __ldg(a.rays + 6 * i + 3 + k); }
+			if (a.hits)
+			{
+				c.hitOut = a.hits + 4 * i;
+				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+			}
+		}
+		const uint32_t colour = march_scene_flat_warp<ST, ALGO, STATS>(c, active, o, d, a.scale);
+		if (active) a.colour[i] = colour;
+	}
+	else if (i < a.n)
 	{
 		float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
 		float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
