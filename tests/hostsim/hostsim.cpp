@@ -112,6 +112,8 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 			c.reset();
 			colour[i] = march<ST, ALGO>(c, rays + 6 * i, rays + 6 * i + 3, scale);
 			if (hits) memcpy(hits + 4 * i, c.hit, 16);
+			#pragma omp atomic
+			gCrawlSkipped += c.st.nCrawlSkipped;
 			local[0] += c.st.nExist; local[1] += c.st.nExistFalse; local[2] += c.st.nLookup; local[3] += c.st.nLookupHit;
 			if (c.st.nLookup > local[4]) local[4] = c.st.nLookup;
 		}
@@ -129,6 +131,7 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 extern "C" {
 
 void sim_set_flat(int flat) { gFlat = flat; }
+int sim_is_flat() { return gFlat; }
 
 // primary_ray_flat's image-plane divisions against IEEE division: every pixel coordinate of an image side of n pixels.
 // Returns the number of mismatches (0 expected).

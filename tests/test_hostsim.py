@@ -141,3 +141,75 @@ def test_exact_reciprocal_divisions_of_the_primary_ray():
     for n in (1, 2, 3, 7, 72, 128, 144, 180, 256, 320, 360, 540, 640, 720, 960, 1000, 1080, 1280, 1920, 2160, 3840, 4096, 7680, 65535, 1 << 20):
         assert lib.sim_check_image_division(n) == 0, n
     assert lib.sim_check_common_division(1, 20_000_000) == 0
+
+
+def pingpong_scene_and_rays():
+    """The reference's second crawl pathology (vrm_flat.cuh pingpong_skip): longest-axis cluster jumps of a ray that sits exactly on
+    a REGION face with one short axis and exactly on a cluster face with the other, both with direction components too small to
+    move it -- it changes region twice per cycle and advances EPSILON per iteration.  Two x two regions with a wall far down
+    the path, rays starting on the region face y = 64 / cluster face z = 24 (and the axis-rolled twins)."""
+    ys, zs = np.meshgrid(np.arange(0, 128, dtype=np.int32), np.arange(0, 128, dtype=np.int32), indexing="ij")
+    wall = np.stack([np.full(ys.size, 61, np.int32), ys.ravel(), zs.ravel()], 1)
+    seeds = np.array([[1, 1, 1], [1, 70, 1], [1, 1, 70], [1, 70, 70]], np.int32)      # make all four regions exist near the start
+    xyz = np.concatenate([wall, seeds])
+    rgb = (np.arange(xyz.shape[0], dtype=np.uint32) * np.uint32(2654435761)) & np.uint32(0xFFFFFF) | np.uint32(0x010101)
+    base = [((2.5, 64.0, 24.0), (0.99982786, -0.017536791, -0.0060571153)),
+            ((3.25, 64.0, 48.0), (0.999665618, -0.0187616404, -0.0177927297)),
+            ((5.125, 64.0, 56.0), (0.999815047, -0.0185558796, -0.00505277468)),
+            ((2.5, 24.0, 64.0), (0.99982786, -0.0060571153, -0.017536791))]
+    rays = [list(o) + list(d) for o, d in base]
+    full_xyz, full_rgb, full_rays = [xyz], [rgb], [np.array(rays, np.float32)]
+    for shift in (1, 2):                       # the same geometry with the axes rolled: every axis takes every role
+        full_xyz.append(np.roll(xyz, shift, axis=1) + np.array([0, 0, 0], np.int32) + 256 * shift)
+        full_rgb.append(rgb)
+        r = np.array(rays, np.float32)
+        r[:, 0:3] = np.roll(r[:, 0:3], shift, axis=1) + 256 * shift
+        r[:, 3:6] = np.roll(r[:, 3:6], shift, axis=1)
+        full_rays.append(r)
+    return np.concatenate(full_xyz).astype(np.int32), np.concatenate(full_rgb), np.concatenate(full_rays).astype(np.float32)
+
+
+def test_core_region_face_pingpong_fast_forward_is_bit_exact():
+    import ctypes as C
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    po.set_lighting("sim")
+    xyz, rgb, rays = pingpong_scene_and_rays()
+    a, b = build_oracle(kind, xyz, rgb, "vcs"), build_oracle("sim", xyz, rgb, "vcs")
+    lib = po._lib("sim")
+    lib.sim_crawl_skipped.restype = C.c_ulonglong
+    lib.sim_crawl_skipped()
+    ta, tb = a.trace_rays(rays, "longestaxis", want_counters=True), b.trace_rays(rays, "longestaxis", want_counters=True)
+    skipped = int(lib.sim_crawl_skipped())
+    assert int(ta["counters"][0]) > 5_000_000           # the reference really does crawl here (twice per cycle across a region face)
+    for k in ("colour", "hits", "counters"):
+        assert np.array_equal(ta[k], tb[k]), k
+    assert (ta["hits"][:, 3] == 1).all()                # every ray ends on the wall
+    if po._lib("sim").sim_is_flat():
+        assert skipped > 0.9 * int(ta["counters"][0])   # ... and the state machine fast-forwarded nearly all of it
+
+
+def test_core_crawl_fast_forward_handles_exact_ties():
+    """EPSILON * d / ulp(position) exactly k + 0.5: the additions round to the even mantissa, a constant even step once the
+    mantissa is even (found on the 2048^3 orbit: 190 000 iterations for one pixel).  Same numbers as that pixel."""
+    import ctypes as C
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    po.set_lighting("sim")
+    ys, zs = np.meshgrid(np.arange(0, 64, dtype=np.int32), np.arange(0, 64, dtype=np.int32), indexing="ij")
+    xyz = np.stack([np.full(ys.size, 62, np.int32), ys.ravel(), zs.ravel()], 1)
+    rgb = np.full(xyz.shape[0], 0x80C0F0, np.uint32)
+    d = (0.848770142, -0.0162127428, -0.528513312)
+    # a cluster skip towards the y = 48 face lands exactly on it (the EPSILON overshoot rounds away); x in [16, 32): EPSILON * d.x = 44.5 ulp
+    rays = np.array([[17.0, 48.02, 46.0, *d], [17.000002, 48.02, 46.0, *d], [9.0, 48.02, 46.0, *d], [33.0, 48.02, 46.0, *d]], np.float32)
+    a, b = build_oracle(kind, xyz, rgb, "vcs"), build_oracle("sim", xyz, rgb, "vcs")
+    lib = po._lib("sim")
+    lib.sim_crawl_skipped.restype = C.c_ulonglong
+    lib.sim_crawl_skipped()
+    for algo in ("original", "longestaxis"):
+        ta, tb = a.trace_rays(rays, algo, want_counters=True), b.trace_rays(rays, algo, want_counters=True)
+        for k in ("colour", "hits", "counters"):
+            assert np.array_equal(ta[k], tb[k]), (algo, k)
+        if algo == "original":
+            assert int(ta["counters"][0]) > 300_000     # ~100 000 iterations per ray in the reference
+            assert int(lib.sim_crawl_skipped()) > 0.9 * int(ta["counters"][0])

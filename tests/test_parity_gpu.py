@@ -385,3 +385,36 @@ def test_scene_generator_argument_errors():
     with pytest.raises(api.VrmError):
         s.generate_terrain(64, 1)                                 # already built
     s.close()
+
+
+def test_region_face_pingpong_and_tie_fast_forwards_are_bit_exact():
+    """The two further forms of the reference's EPSILON crawl (tests/test_hostsim.py has the scenes): rays hopping across a region
+    face twice per cycle (pingpong_skip) and crawl steps that are exact rounding ties (crawl_skip).  Oracle = millions of
+    iterations; the kernels fast-forward them and must return the same colours, hit voxels and event counters."""
+    from tests.test_hostsim import pingpong_scene_and_rays
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    xyz, rgb, rays = pingpong_scene_and_rays()
+    s, ref = build_product(xyz, rgb, "vcs"), build_oracle(kind, xyz, rgb, "vcs")
+    s.set_statistics(True)
+    got, want = s.trace_rays(rays, "longestaxis", want_hits=True), ref.trace_rays(rays, "longestaxis", want_counters=True)
+    st = s.get_statistics()
+    assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"])
+    assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3])
+    assert st["crawl_skipped"] > 0.9 * st["exist_checks"] > 4_000_000
+    s.close()
+    ys, zs = np.meshgrid(np.arange(0, 64, dtype=np.int32), np.arange(0, 64, dtype=np.int32), indexing="ij")
+    xyz = np.stack([np.full(ys.size, 62, np.int32), ys.ravel(), zs.ravel()], 1)
+    rgb = np.full(xyz.shape[0], 0x80C0F0, np.uint32)
+    d = (0.848770142, -0.0162127428, -0.528513312)
+    rays = np.array([[17.0, 48.02, 46.0, *d], [17.000002, 48.02, 46.0, *d], [9.0, 48.02, 46.0, *d], [33.0, 48.02, 46.0, *d]], np.float32)
+    s, ref = build_product(xyz, rgb, "vcs"), build_oracle(kind, xyz, rgb, "vcs")
+    s.set_statistics(True)
+    for algo in ("original", "longestaxis"):
+        got, want = s.trace_rays(rays, algo, want_hits=True), ref.trace_rays(rays, algo, want_counters=True)
+        st = s.get_statistics()
+        assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"]), algo
+        assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3]), algo
+        if algo == "original":
+            assert st["crawl_skipped"] > 0.9 * st["exist_checks"] > 250_000
+    s.close()

@@ -194,7 +194,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (VoxelChunk& c : s->chunks) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); }
 	vrm_free_structure(s);
-	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue);
+	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer);
 	if (s->h_cams) cudaFreeHost(s->h_cams);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);

@@ -342,11 +342,14 @@ template <int ST, bool STATS> struct RayCtx
 	// of the hit map, so no registers stay live for it; the host harness points it at hit[]).
 	int32_t* hitOut;
 	int32_t hit[4];
+	// Queue of rays handed to the resume kernel (vrm_flat.cuh kPpDefer, vrm_render.cu resume_kernel); null = none
+	void* deferQueue;
 	Stats st;
 
 	VRM_HD void reset()
 	{
 		hit[0] = hit[1] = hit[2] = hit[3] = 0;
+		deferQueue = nullptr;
 		if (STATS) { st.nExist = st.nExistFalse = st.nLookup = st.nLookupHit = st.nProbe2 = st.nRegionReads = st.nCrawlSkipped = 0; }
 	}
 };
@@ -567,7 +570,7 @@ VRM_HD float bits_float(uint32_t u)
 // crawl the same way.
 // While the ray stays inside the cluster cell, each iteration is exactly  o_i <- RN(o_i + c_i),  c_i = RN(EPSILON * d_i).
 // Inside one binade a float advances by a constant whole number q_i of ulps per such addition (q_i = nearest integer to
-// c_i / ulp; exact ties are excluded), i.e. its bit pattern advances by q_i.  So M iterations are one integer multiply-add
+// c_i / ulp; on an exact tie the even one of the two neighbours, once the mantissa is even), i.e. its bit pattern advances by q_i.  So M iterations are one integer multiply-add
 // per axis: the result is bit-identical to executing them.  M is chosen so that all M skipped positions stay strictly
 // inside the cell and the binade; the step that leaves the cell is then executed normally.
 // Returns M (0 = nothing skipped).  v = voxel whose cluster is being skipped; the caller guarantees (int)o lies in that cell.
@@ -587,8 +590,18 @@ VRM_HD int crawl_skip(float* o, const float* dir, float thr, int v0, int v1, int
 		const float c = vmul(kEps, dir[i]);
 		const float cu = vmul(c, bits_float((277u - eb) << 23));  // c / ulp(y), exact power-of-two scaling
 		if (!(fabsf(cu) < 1048576.0f)) return 0;
-		if (vsub(cu, floorf(cu)) == 0.5f) return 0;  // exact tie: the additions alternate between two step sizes
-		const int qi = (int)rintf(cu);
+		int qi;
+		const float cuFloor = floorf(cu);
+		if (vsub(cu, cuFloor) == 0.5f)
+		{
+			// exact tie: y + c lies midway between two floats and rounds to the one with the even mantissa.  From an even
+			// mantissa that is the even one of {floor(cu), floor(cu) + 1} ulps, and the mantissa stays even, so the step is
+			// constant from then on; from an odd mantissa one ordinary step makes it even (no skip this time)
+			if (yb & 1u) return 0;
+			const int k = (int)cuFloor;
+			qi = (k & 1) ? k + 1 : k;
+		}
+		else qi = (int)rintf(cu);
 		const int cell = v[i] & ~7;
 		uint32_t lo = float_bits((float)cell), hi = float_bits((float)(cell + 8));
 		const uint32_t blo = eb << 23, bhi = (eb + 1u) << 23;

@@ -30,6 +30,13 @@
 
 // 1: the state machine's VCS test site reads the cluster-exists flag from the header word it needs anyway (one load);
 // 0: separate 64-byte-per-region cluster mask first (two dependent loads, but empty clusters never touch the headers)
+// cold member functions of the state machine: out of line on the device (they copy the whole ray state)
+#if defined(__CUDACC__)
+#define VRM_FLAT_COLD __host__ __device__ __noinline__
+#else
+#define VRM_FLAT_COLD
+#endif
+
 #ifndef VRM_VCS_FUSED_EXIST
 #define VRM_VCS_FUSED_EXIST 1
 #endif
@@ -43,7 +50,8 @@ enum FlatState : int
 	kStRegion = 1,
 	kStHead = 2,
 	kStHit = 3,
-	kStDone = 4
+	kStDone = 4,
+	kStPark = 5   // kPpDefer: the ray met the ping-pong pathology; its lane stops and the caller parks it for resume_kernel
 };
 
 // What the advance of a kStMain step moves to.  All are "t_i = (next_i - o_i) / dir_i, o += (min t [+ EPSILON]) * dir".
@@ -63,6 +71,22 @@ constexpr uint32_t kFlEq0 = 4u;          // t_i == tMin of the last kAdvNext / k
 constexpr uint32_t kFlEqMask = 28u;
 constexpr int kFlPermShift = 8;
 constexpr int32_t kRiPending = -3;       // FlatRay::ri: the ray has left its region, rebase + table read still to do          // bits 8-13: world axis of walk slot 0 / 1 / 2, two bits each
+
+// What a ray does when it meets the region-face ping-pong pathology (FlatRay::pingpong_skip):
+//   kPpOff     nothing: it crawls like the reference
+//   kPpDefer   it parks its whole state in a device queue and its lane finishes; resume_kernel (vrm_render.cu) continues such
+//              rays with kPpInline.  This keeps the fast-forward (which copies the ray state and calls out of line) away from
+//              the hot kernels: compiled into them -- even as a never-taken branch -- it cost 30 % of their speed.
+//   kPpInline  fast-forward in place (resume kernel, host harness)
+constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
+constexpr int kPpDefault = kPpInline;  // single-ray callers (host harness); the kernels name their policy
+
+struct DeferHeader
+{
+	unsigned int count;     // rays queued (may exceed capacity: the excess was not queued)
+	unsigned int capacity;
+	unsigned int pad[2];
+};
 
 VRM_HD PermRuntime unpack_perm(uint32_t fl)
 {
@@ -398,6 +422,8 @@ struct FlatRay
 	}
 
 	// ---- kStMain: [one advance] + one voxel test ------------------------------------------------------------------------
+	// NOSKIP: plain execution without the crawl / ping-pong fast-forwards (the fast-forwards use it to probe cycles)
+	template <bool NOSKIP = false, int PP = kPpDefault>
 	VRM_HD void do_main(RayCtx<ST, STATS>& c)
 	{
 		int slot = 0;
@@ -431,11 +457,20 @@ struct FlatRay
 			const bool gd = skip ? shadowOriginal() : (jump ? false : shadow());
 			if (gd) { a0 = (e0 != 0.0f) ? a0 : INFINITY; a1 = (e1 != 0.0f) ? a1 : INFINITY; a2 = (e2 != 0.0f) ? a2 : INFINITY; }
 			float m = min3(a0, a1, a2);
-			if (m == 0.0f && (mode == kAdvCluster || jump))
+			if (!NOSKIP && m == 0.0f && (mode == kAdvCluster || jump))
 			{
 				// the ray sits on a cluster face it cannot leave: fast-forward the EPSILON crawl (crawl_skip, vrm_core.cuh)
 				const CrawlResult cr = crawl_skip_cold(o[0], o[1], o[2], e0, e1, e2, thr, g[0], g[1], g[2]);
 				const int skipped = cr.skipped;
+				if constexpr (kLA && ST == kStorageVcs && PP != kPpOff)
+				{
+					// ... or it also sits exactly on a REGION face and hops between the two regions every iteration (pingpong_skip)
+					if (skipped == 0 && jump && (o[1] == 0.0f || o[1] == (float)kRegion || o[2] == 0.0f || o[2] == (float)kRegion))
+					{
+						if constexpr (PP == kPpInline) { if (pingpong_skip(c)) return; }
+						else { if (c.deferQueue) { st = kStPark; return; } }  // nothing has been changed yet: the resume kernel redoes this step
+					}
+				}
 				if (skipped > 0)
 				{
 					o[0] = cr.o0; o[1] = cr.o1; o[2] = cr.o2;
@@ -543,22 +578,187 @@ struct FlatRay
 		}
 	}
 
+	// ---- kPpDefer: park the ray in the device queue ---------------------------------------------------------------------------
+	struct Deferred
+	{
+		FlatRay ray;
+		int32_t* hitOut;               // the pixel's hit-map slot (or null), from the context
+		unsigned long long outAddr;    // where the colour goes: filled in by the kernel that queued the ray
+		uint32_t outKind;              // 0: three RGB8 bytes, 1: one uint32 colour
+		uint32_t pad;
+	};
+	// Called by the marching wrappers AFTER their loop for a ray that stopped in kStPark.  Returns the queue slot, or -1 when the
+	// queue is full (the ray is then back in kStMain and the caller lets it crawl on like the reference).
+	VRM_HD int park(RayCtx<ST, STATS>& c)
+	{
+#if defined(__CUDA_ARCH__)
+		DeferHeader* h = static_cast<DeferHeader*>(c.deferQueue);
+		const unsigned int slot = atomicAdd(&h->count, 1u);
+		st = kStMain;
+		if (slot >= h->capacity) return -1;
+		Deferred* items = reinterpret_cast<Deferred*>(h + 1);
+		items[slot].ray = *this;
+		items[slot].hitOut = c.hitOut;
+		items[slot].outAddr = 0ull;
+		st = kStDone;
+		return (int)slot;
+#else
+		st = kStMain;
+		return -1;
+#endif
+	}
+
+	// ---- region-face ping-pong fast-forward ---------------------------------------------------------------------------------
+	// A second form of the reference's EPSILON crawl (vrm_core.cuh crawl_skip has the first).  Longest-axis cluster jump, one of
+	// the short axes stuck on a cluster face (t = 0, so every jump iteration advances by EPSILON * direction only) and the other
+	// short axis sitting exactly on a REGION face with a direction component too small to move it: the ray leaves the region
+	// by a rounding error, is rebased to local 64 (or 0) in the neighbouring region, runs that region's prologue, loop head and
+	// first voxel test (empty cluster), jumps again, leaves again ... two region changes per cycle, ~10^4 cycles per voxel of
+	// progress along the longest axis, 10^5-10^6 iterations per ray (4 such pixels made a 1080p frame of the 2048^3 orbit take
+	// 710 ms instead of ~2 ms; the reference's own kernels crawl the same way).
+	// Per cycle only the longest-axis coordinate changes, by a constant number of ulps (as in crawl_skip); every decision of the
+	// cycle is a monotone function of that coordinate (rounded sums / products with constants, truncations, comparisons).  So
+	// if the FIRST and the LAST cycle of a span -- both executed here with the ordinary code on a copy of the ray -- take the
+	// same decisions, every cycle in between does, and the ray can be moved to the end of the span: bit-identical to executing
+	// the cycles.  The span keeps the coordinate inside its voxel and its binade.
+	struct Discrete
+	{
+		int st, mode, g0, g1, g2, ad1, ad2;
+		int32_t ri;
+		uint32_t ur0, ur1, ur2, seq, fl, o1, o2;
+	};
+	VRM_HD Discrete discrete() const
+	{
+		Discrete k;
+		k.st = st; k.mode = mode; k.g0 = g[0]; k.g1 = g[1]; k.g2 = g[2]; k.ad1 = ad1; k.ad2 = ad2; k.ri = ri;
+		k.ur0 = ur[0]; k.ur1 = ur[1]; k.ur2 = ur[2]; k.seq = seq; k.fl = fl & ~kFlEqMask; k.o1 = float_bits(o[1]); k.o2 = float_bits(o[2]);
+		return k;
+	}
+	static VRM_HD bool same_discrete(const Discrete& a, const Discrete& b)
+	{
+		return a.st == b.st && a.mode == b.mode && a.g0 == b.g0 && a.g1 == b.g1 && a.g2 == b.g2 && a.ad1 == b.ad1 && a.ad2 == b.ad2 && a.ri == b.ri &&
+		       a.ur0 == b.ur0 && a.ur1 == b.ur1 && a.ur2 == b.ur2 && a.seq == b.seq && a.fl == b.fl && a.o1 == b.o1 && a.o2 == b.o2;
+	}
+
+	// One half cycle, executed plainly: jump advance that leaves the region -> region entry -> prologue -> head -> first voxel
+	// test, which must send the ray back into a jump.
+	VRM_HD bool pingpong_half(RayCtx<ST, STATS>& c)
+	{
+		if constexpr (kLA)
+		{
+			if (!(st == kStMain && mode == kAdvJump)) return false;
+			do_main<true>(c);
+			if (st != kStRegion) return false;
+			do_region(c);
+			if (st != kStHead) return false;
+			do_head();
+			if (!(st == kStMain && mode == kAdvNone)) return false;
+			do_main<true>(c);
+			return st == kStMain && mode == kAdvJump;
+		}
+		return false;
+	}
+
+	// Returns true when the ray was moved forward by whole cycles (it is then again in kStMain / kAdvJump, before an advance).
+	VRM_FLAT_COLD bool pingpong_skip(RayCtx<ST, STATS>& c)
+	{
+		if (!(thr == thr)) return false;
+		const uint32_t xb = float_bits(o[0]), eb = xb >> 23;
+		if (eb < 24u || eb > 140u) return false;
+		const float c0 = vmul(kEps, sd[0]);
+		const float cu = vmul(c0, bits_float((277u - eb) << 23));  // advance per iteration in ulps of o[0]
+		if (!(fabsf(cu) < 1048576.0f)) return false;
+		int q;
+		const float cuFloor = floorf(cu);
+		if (vsub(cu, cuFloor) == 0.5f)
+		{
+			if (xb & 1u) return false;  // exact tie from an odd mantissa: one ordinary iteration makes it even (see crawl_skip)
+			const int k = (int)cuFloor;
+			q = (k & 1) ? k + 1 : k;
+		}
+		else q = (int)rintf(cu);
+		if (q == 0) return false;
+		// o[0] must stay strictly inside its voxel (the prologue truncates it) and its binade (constant ulp)
+		const int v0 = (int)o[0];
+		uint32_t lo = float_bits((float)v0), hi = float_bits((float)(v0 + 1));
+		const uint32_t blo = eb << 23, bhi = (eb + 1u) << 23;
+		if (lo < blo) lo = blo;
+		if (hi > bhi) hi = bhi;
+		if (xb < lo || xb >= hi) return false;
+		const uint32_t room = q > 0 ? (hi - 1u - xb) / (uint32_t)q : (xb - lo) / (uint32_t)(-q);  // advances that keep o[0] inside
+		const uint32_t cycles = room / 2u;  // whole cycles that keep o[0] inside
+		if (cycles < 4u) return false;
+		const FlatRay start = *this;
+		const Stats saved = c.st;
+		const Discrete k0 = discrete();
+		bool ok = pingpong_half(c);
+		const Discrete kA = discrete();
+		const uint32_t xA = float_bits(o[0]);
+		ok = ok && (int32_t)(xA - xb) == q && pingpong_half(c);
+		const Discrete kB = discrete();
+		ok = ok && (int32_t)(float_bits(o[0]) - xA) == q && same_discrete(kB, k0);
+		const Stats per = c.st;
+		// Cycle number m (1-based) starts (m - 1) cycles after `start`.  "Cycle m takes the decisions of cycle 1" is monotone in m
+		// (see above), so the cycles that do form a prefix 1..good: binary search for its end with one probed cycle per step.
+		uint32_t good = 1u, bad = cycles + 1u;
+		while (ok && bad - good > 1u)
+		{
+			const uint32_t mid = good + (bad - good) / 2u;
+			*this = start;
+			const uint32_t xl = xb + (mid - 1u) * 2u * (uint32_t)q;
+			o[0] = bits_float(xl);
+			bool same = pingpong_half(c) && same_discrete(discrete(), kA) && (int32_t)(float_bits(o[0]) - xl) == q;
+			const uint32_t xm = float_bits(o[0]);
+			same = same && pingpong_half(c) && same_discrete(discrete(), kB) && (int32_t)(float_bits(o[0]) - xm) == q;
+			if (same) good = mid; else bad = mid;
+		}
+		if (ok && good >= 3u)
+		{
+			// the state after `good` cycles: execute cycle `good` once more (plainly) from its start
+			*this = start;
+			o[0] = bits_float(xb + (good - 1u) * 2u * (uint32_t)q);
+			ok = pingpong_half(c) && pingpong_half(c);
+		}
+		else ok = false;
+		if (!ok)
+		{
+			*this = start;
+			c.st = saved;
+			return false;
+		}
+		const uint32_t done = good;
+		if (STATS)
+		{
+			// counters: `done` times what one cycle added
+			const unsigned long long n = done;
+			Stats t = saved;
+			t.nExist += n * (per.nExist - saved.nExist); t.nExistFalse += n * (per.nExistFalse - saved.nExistFalse);
+			t.nLookup += n * (per.nLookup - saved.nLookup); t.nLookupHit += n * (per.nLookupHit - saved.nLookupHit);
+			t.nProbe2 += n * (per.nProbe2 - saved.nProbe2); t.nRegionReads += n * (per.nRegionReads - saved.nRegionReads);
+			t.nCrawlSkipped = saved.nCrawlSkipped + n * (per.nExist - saved.nExist);
+			c.st = t;
+		}
+		return true;
+	}
+
 	// Run the blocks the ray's state asks for, in program order.  Returns true when the pixel is resolved.
+	template <int PP = kPpDefault>
 	VRM_HD bool step(RayCtx<ST, STATS>& c)
 	{
 		if (st == kStHit) do_hit(c);
 		if (st == kStRegion) do_region(c);
 		if constexpr (kLA) { if (st == kStHead) do_head(); }
-		if (st == kStMain) do_main(c);
+		if (st == kStMain) do_main<false, PP>(c);
 		return st == kStDone;
 	}
 
 	// the marching blocks only (region -> head -> main); hits are shaded by the caller
+	template <int PP = kPpDefault>
 	VRM_HD void step_marching(RayCtx<ST, STATS>& c)
 	{
 		if (st == kStRegion) do_region(c);
 		if constexpr (kLA) { if (st == kStHead) do_head(); }
-		if (st == kStMain) do_main(c);
+		if (st == kStMain) do_main<false, PP>(c);
 	}
 };
 
@@ -569,8 +769,9 @@ struct FlatRay
 // neighbouring origins, so they walk in lockstep instead of being interleaved with late primary rays (measured on the 4K
 // terrain frame, VCS + longest axis: 1.62 -> 1.53 ms; a further barrier at region changes measured no gain and was dropped).
 // Only the interleaving of different rays' operations changes; every ray executes exactly the operations it always did.
-template <int ST, int ALGO, bool STATS>
-VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const float* originW, const float* dirW, float scale)
+// deferredSlot: the ray's slot in the defer queue when it was parked there (its colour is then not final), else -1
+template <int ST, int ALGO, bool STATS, int PP>
+VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const float* originW, const float* dirW, float scale, int& deferredSlot)
 {
 	FlatRay<ST, ALGO, STATS> ray;
 	ray.st = kStDone; ray.result = 0;
@@ -578,30 +779,51 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 #if defined(__CUDA_ARCH__)
 	for (;;)
 	{
-		const unsigned marching = __ballot_sync(0xFFFFFFFFu, ray.st == kStMain || ray.st == kStHead || ray.st == kStRegion);
+		const unsigned marching = __ballot_sync(0xFFFFFFFFu, ray.st <= kStHead);  // kStMain, kStRegion, kStHead
 		if (marching != 0u)
 		{
-			if (ray.st != kStHit && ray.st != kStDone) ray.step_marching(c);
+			if (ray.st <= kStHead) ray.template step_marching<PP>(c);
 			continue;
 		}
-		// nobody is marching: every lane is waiting with a hit or is done
+		// nobody is marching: every lane is waiting with a hit, done or parked
 		if (!__any_sync(0xFFFFFFFFu, ray.st == kStHit)) break;
 		if (ray.st == kStHit) ray.do_hit(c);
 	}
 #else
-	while (ray.st != kStDone) ray.step(c);
+	while (ray.st < kStDone) ray.template step<PP>(c);
 #endif
+	deferredSlot = -1;
+	if (ray.st == kStPark)
+	{
+		deferredSlot = ray.park(c);
+		if (deferredSlot < 0) { while (ray.st < kStDone) ray.template step<kPpOff>(c); }  // queue full: crawl on like the reference
+		else ray.result = 0u;
+	}
 	return ray.result;
 }
 
 // Convenience for single-ray callers (trace kernels, host sim): run the state machine to completion.
-template <int ST, int ALGO, bool STATS>
-VRM_HD uint32_t march_scene_flat(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
+template <int ST, int ALGO, bool STATS, int PP = kPpDefault>
+VRM_HD uint32_t march_scene_flat(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale, int& deferredSlot)
 {
 	FlatRay<ST, ALGO, STATS> ray;
 	ray.start_primary(c, originW, dirW, scale);
-	while (ray.st != kStDone) ray.step(c);
+	while (ray.st < kStDone) ray.template step<PP>(c);
+	deferredSlot = -1;
+	if (ray.st == kStPark)
+	{
+		deferredSlot = ray.park(c);
+		if (deferredSlot < 0) { while (ray.st < kStDone) ray.template step<kPpOff>(c); }  // queue full: crawl on like the reference
+		else ray.result = 0u;
+	}
 	return ray.result;
+}
+
+template <int ST, int ALGO, bool STATS>
+VRM_HD uint32_t march_scene_flat(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
+{
+	int unused;
+	return march_scene_flat<ST, ALGO, STATS, kPpDefault>(c, originW, dirW, scale, unused);
 }
 
 }  // namespace vrm

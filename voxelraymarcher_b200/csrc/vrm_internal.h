@@ -56,6 +56,7 @@ struct vrm_scene
 	size_t viewBatchBytes = size_t(256) << 20;  // device bytes per batch buffer (VRM_VIEW_BATCH_BYTES)
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
+	void* d_defer = nullptr;          // rays parked for resume_kernel (vrm_render.cu): DeferHeader + records
 	int numSms = 148;
 	int renderMode = -1;              // -1 = per-combination default (vrm_render.cu); 0 = scheduled persistent kernel, 1 = nested loops, 2 = per-lane state machine (VRM_RENDER_MODE)
 

@@ -59,6 +59,7 @@ struct RenderArgs
 	uint8_t* rgb;       // nViews x H x W x 3
 	int32_t* hits;      // nullable, nViews x H x W x 4
 	Stats* stats;       // nullable
+	void* defer;        // DeferHeader + records: rays parked for resume_kernel (vrm_flat.cuh kPpDefer)
 	unsigned int* queue;   // persistent kernel: next unclaimed pixel slot
 	uint32_t tilesX, tilesPerView, nViews;
 };
@@ -76,6 +77,65 @@ __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* o
 			for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
 			if ((threadIdx.x & 31) == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(out) + k, x);
 		}
+	}
+}
+
+// a ray parked by FlatRay::defer: tell the resume kernel where its colour goes
+template <class Ray>
+__device__ __forceinline__ void park_output(void* queue, int slot, const void* out, uint32_t kind)
+{
+	typename Ray::Deferred* items = reinterpret_cast<typename Ray::Deferred*>(static_cast<DeferHeader*>(queue) + 1);
+	items[slot].outAddr = reinterpret_cast<unsigned long long>(out);
+	items[slot].outKind = kind;
+}
+
+struct ResumeArgs
+{
+	SceneView sv;
+	Lighting light;
+	LightWalk lw;
+	float translation[3];
+	Stats* stats;
+	void* defer;
+};
+
+// Continues the rays the render / trace kernels parked (region-face ping-pong, vrm_flat.cuh): a handful per frame at most,
+// each worth 10^5-10^6 iterations of the reference, fast-forwarded here in place.  One thread per ray; ONE block, which also
+// re-arms the queue for the next launch (so the render path needs no memset).
+constexpr int kResumeThreads = 256;
+template <int ST, int ALGO, bool STATS>
+__global__ void __launch_bounds__(kResumeThreads) resume_kernel(const ResumeArgs a)
+{
+	using Ray = FlatRay<ST, ALGO, STATS>;
+	DeferHeader* h = static_cast<DeferHeader*>(a.defer);
+	typename Ray::Deferred* items = reinterpret_cast<typename Ray::Deferred*>(h + 1);
+	const unsigned int n = h->count < h->capacity ? h->count : h->capacity;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.lw = a.lw;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		Ray ray = items[i].ray;
+		c.hitOut = items[i].hitOut;
+		while (ray.st != kStDone) ray.template step<kPpInline>(c);
+		const uint32_t color = ray.result;
+		if (items[i].outKind == 0u)
+		{
+			uint8_t* px = reinterpret_cast<uint8_t*>(items[i].outAddr);
+			px[0] = (uint8_t)(color >> 16); px[1] = (uint8_t)((color >> 8) & 0xFF); px[2] = (uint8_t)(color & 0xFF);
+		}
+		else *reinterpret_cast<uint32_t*>(items[i].outAddr) = color;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) h->count = 0u;
+	if constexpr (STATS)
+	{
+		// lanes leave the loop together (uniform trip count per warp is not guaranteed): plain atomics
+		unsigned long long v[7] = {c.st.nExist, c.st.nExistFalse, c.st.nLookup, c.st.nLookupHit, c.st.nProbe2, c.st.nRegionReads, c.st.nCrawlSkipped};
+		for (int k = 0; k < 7; k++) if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats) + k, v[k]);
 	}
 }
 
@@ -116,7 +176,10 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
 		}
-		color = march_scene_flat_warp<ST, ALGO, STATS>(c, inside, o, d, a.scale);
+		c.deferQueue = a.defer;
+		int slot;
+		color = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, slot);
+		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (((size_t)blockIdx.z * a.H + y) * a.W + x), 0u);
 	}
 	else if (inside)
 	{
@@ -137,7 +200,10 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 				c.hitOut = a.hits + 4 * (((size_t)blockIdx.z * a.H + y) * a.W + x);
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
-			color = march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale);
+			c.deferQueue = a.defer;
+			int slot;
+			color = march_scene_flat<ST, ALGO, STATS, kPpDefer>(c, o, d, a.scale, slot);
+			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (((size_t)blockIdx.z * a.H + y) * a.W + x), 0u);
 		}
 		else
 		{
@@ -268,7 +334,7 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 		}
 		if (st == run)
 		{
-			if (run == kStMain) ray.do_main(c);
+			if (run == kStMain) ray.template do_main<false, kPpOff>(c);
 			else if (run == kStRegion) ray.do_region(c);
 			else if (run == kStHit) ray.do_hit(c);
 			else if constexpr (ALGO != kAlgoOriginal) ray.do_head();
@@ -297,6 +363,7 @@ struct TraceArgs
 	uint32_t* colour;
 	int32_t* hits;
 	Stats* stats;
+	void* defer;
 };
 
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
@@ -324,8 +391,11 @@ __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
 		}
-		const uint32_t colour = march_scene_flat_warp<ST, ALGO, STATS>(c, active, o, d, a.scale);
+		c.deferQueue = a.defer;
+		int slot;
+		const uint32_t colour = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, active, o, d, a.scale, slot);
 		if (active) a.colour[i] = colour;
+		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + i, 1u);
 	}
 	else if (i < a.n)
 	{
@@ -338,7 +408,10 @@ __global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
 				c.hitOut = a.hits + 4 * i;
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
-			a.colour[i] = march_scene_flat<ST, ALGO, STATS>(c, o, d, a.scale);
+			c.deferQueue = a.defer;
+			int slot;
+			a.colour[i] = march_scene_flat<ST, ALGO, STATS, kPpDefer>(c, o, d, a.scale, slot);
+			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + i, 1u);
 		}
 		else
 		{
@@ -383,9 +456,43 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 	a.translation[0] = translation[0]; a.translation[1] = translation[1]; a.translation[2] = translation[2];
 	a.scale = static_cast<float>(scale);  // Ray.cuh:16
 	a.stats = s->statsEnabled ? s->d_stats : nullptr;
+	a.defer = nullptr;
 }
 
-template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs& a, dim3 grid)
+constexpr unsigned int kDeferCapacity = 16384;  // parked rays per launch (a 4K frame of the 2048^3 orbit parks a few dozen)
+
+// The queue exists only for VCS + longest axis (the one combination that can ping-pong): reset its counter before the launch.
+template <int ST, int ALGO> void* prepare_defer_queue(vrm_scene* s)
+{
+	if constexpr (!(ST == kStorageVcs && ALGO != kAlgoOriginal)) return nullptr;
+	using Rec = typename FlatRay<ST, ALGO, false>::Deferred;
+	static_assert(sizeof(Rec) == sizeof(typename FlatRay<ST, ALGO, true>::Deferred), "one queue layout for both statistics modes");
+	if (!s->d_defer)
+	{
+		const size_t bytes = sizeof(DeferHeader) + (size_t)kDeferCapacity * sizeof(Rec);
+		if (cudaMalloc(&s->d_defer, bytes) != cudaSuccess) { cudaGetLastError(); s->d_defer = nullptr; return nullptr; }  // no queue: such rays crawl like the reference
+		const DeferHeader h = {0u, kDeferCapacity, {0u, 0u}};
+		cudaMemcpyAsync(s->d_defer, &h, sizeof(h), cudaMemcpyHostToDevice, s->stream);
+		cudaStreamSynchronize(s->stream);
+	}
+	return s->d_defer;  // its counter is zero: resume_kernel re-arms it after every launch
+}
+
+template <int ST, int ALGO, class Args> void launch_resume(vrm_scene* s, const Args& a)
+{
+	if constexpr (ST == kStorageVcs && ALGO != kAlgoOriginal)
+	{
+		if (!a.defer) return;
+		ResumeArgs r;
+		r.sv = a.sv; r.light = a.light; r.lw = a.lw;
+		r.translation[0] = a.translation[0]; r.translation[1] = a.translation[1]; r.translation[2] = a.translation[2];
+		r.stats = a.stats; r.defer = a.defer;
+		if (s->statsEnabled) resume_kernel<ST, ALGO, true><<<1, kResumeThreads, 0, s->stream>>>(r);
+		else resume_kernel<ST, ALGO, false><<<1, kResumeThreads, 0, s->stream>>>(r);
+	}
+}
+
+template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim3 grid)
 {
 	// Which form of the traversal runs is a measured choice per combination (512^3 terrain, 4K, B200):
 	// the per-lane state machine wins where cluster jumps nest inside the longest-axis loop (VCS + longest axis: 2.06 ms
@@ -397,10 +504,12 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs&
 		else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		return;
 	}
-	if (mode == 2)  // state machine per lane, one CTA per 32x8 pixels, no ray queue
+	if (mode == 2)  // state machine per lane, one CTA per 32x4 pixels
 	{
+		a.defer = prepare_defer_queue<ST, ALGO>(s);
 		if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		launch_resume<ST, ALGO>(s, a);
 		return;
 	}
 	// persistent kernel: as many CTAs as fit on the device at once (a multiple of the SM count)
@@ -418,7 +527,7 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, const RenderArgs&
 	else render_scheduled_kernel<ST, ALGO, false><<<blocks, kPersistThreads, 0, s->stream>>>(a);
 }
 
-template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a, unsigned grid)
+template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsigned grid)
 {
 	// Arbitrary (incoherent) rays: the per-lane state machine measured faster than the nested loops for every combination
 	// (1024^3 sparse shells, 8.3 M random rays: original 11.7 vs 21.1 ms, longest axis 28.4 vs 31.2 ms), so it is the
@@ -426,8 +535,10 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, const TraceArgs& a
 	const int mode = s->renderMode == 1 ? 1 : 2;
 	if (mode == 2)
 	{
+		a.defer = prepare_defer_queue<ST, ALGO>(s);
 		if (s->statsEnabled) trace_kernel<ST, ALGO, true, true><<<grid, 256, 0, s->stream>>>(a);
 		else trace_kernel<ST, ALGO, false, true><<<grid, 256, 0, s->stream>>>(a);
+		launch_resume<ST, ALGO>(s, a);
 	}
 	else
 	{
