@@ -793,11 +793,14 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 	while (ray.st < kStDone) ray.template step<PP>(c);
 #endif
 	deferredSlot = -1;
-	if (ray.st == kStPark)
+	if constexpr (PP == kPpDefer && ST == kStorageVcs && ALGO != kAlgoOriginal)  // the only combination that can park (do_main)
 	{
-		deferredSlot = ray.park(c);
-		if (deferredSlot < 0) { while (ray.st < kStDone) ray.template step<kPpOff>(c); }  // queue full: crawl on like the reference
-		else ray.result = 0u;
+		if (ray.st == kStPark)
+		{
+			deferredSlot = ray.park(c);
+			if (deferredSlot < 0) { while (ray.st < kStDone) ray.template step<kPpOff>(c); }  // queue full: crawl on like the reference
+			else ray.result = 0u;
+		}
 	}
 	return ray.result;
 }
@@ -810,11 +813,14 @@ VRM_HD uint32_t march_scene_flat(RayCtx<ST, STATS>& c, const float* originW, con
 	ray.start_primary(c, originW, dirW, scale);
 	while (ray.st < kStDone) ray.template step<PP>(c);
 	deferredSlot = -1;
-	if (ray.st == kStPark)
+	if constexpr (PP == kPpDefer && ST == kStorageVcs && ALGO != kAlgoOriginal)  // the only combination that can park (do_main)
 	{
-		deferredSlot = ray.park(c);
-		if (deferredSlot < 0) { while (ray.st < kStDone) ray.template step<kPpOff>(c); }  // queue full: crawl on like the reference
-		else ray.result = 0u;
+		if (ray.st == kStPark)
+		{
+			deferredSlot = ray.park(c);
+			if (deferredSlot < 0) { while (ray.st < kStDone) ray.template step<kPpOff>(c); }  // queue full: crawl on like the reference
+			else ray.result = 0u;
+		}
 	}
 	return ray.result;
 }

@@ -366,8 +366,16 @@ struct TraceArgs
 	void* defer;
 };
 
+// Incoherent rays are latency-bound: occupancy is worth more than a few spilled registers (measured, 1024^3 shells, 8.3 M rays:
+// VCS + original 9.37 ms at 54 registers / 4 CTAs, 8.82 at 48 / 5, 8.31 at 40 / 6; VCS + longest axis 16.77 at 78 / 3, 14.14 at 64 / 4, 14.50 at 48 / 5).
+#ifndef VRM_TRACE_LA_MINBLOCKS
+#define VRM_TRACE_LA_MINBLOCKS 4
+#endif
+#ifndef VRM_TRACE_ORIG_MINBLOCKS
+#define VRM_TRACE_ORIG_MINBLOCKS 6
+#endif
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
-__global__ void __launch_bounds__(256) trace_kernel(const TraceArgs a)
+__global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MINBLOCKS : VRM_TRACE_LA_MINBLOCKS) trace_kernel(const TraceArgs a)
 {
 	unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
 	RayCtx<ST, STATS> c;
