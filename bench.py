@@ -339,7 +339,8 @@ def main():
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": WIDTH * HEIGHT * 3},
-            "gpu_launches": args.steps, "roofline": roofline, "exchange": exchange, "exchange_verified": exchange_ok,
+            "gpu_launches": 2 * args.steps,   # per step: render_kernel + the one-block resume_kernel behind it (parked rays; ~3 us)
+            "roofline": roofline, "exchange": exchange, "exchange_verified": exchange_ok,
             "ms_per_frame_kernel": tk_ms / args.steps, "value_without_gather": value_no_gather, "wall_s_timed_region": wall,
             "build": {"ms": build_ms, "mvoxels_per_s": xyz.shape[0] / build_ms / 1e3, "voxels": int(xyz.shape[0]), "unique_voxels": info["unique_voxels"],
                       "regions": info["filled"], "structure_bytes": info["bytes"]},

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kResumeThreads) resume_kernel(const ResumeArgs
 }
 
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
-__global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? 5 : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? (ALGO == kAlgoOriginal ? 6 : 5) : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lx = (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1)), ly = (warp / kBlockTilesX) * kTileH + (lane / kTileW);
