@@ -87,6 +87,11 @@ int vrm_scene_add_voxels_device(vrm_scene* scene, const int32_t* d_xyz, const ui
  * Legal only before vrm_scene_build; can be mixed with vrm_scene_add_voxels. */
 int vrm_scene_generate_terrain(vrm_scene* scene, uint32_t size, uint32_t seed, uint32_t max_height, uint64_t* n_out);
 int vrm_scene_generate_sparse_shells(vrm_scene* scene, uint32_t size, uint32_t cell, uint32_t seed, uint32_t fill_pct, uint64_t* n_out);
+/* The reference's own generators on the GPU, voxel for voxel and IN ITS INSERTION ORDER (overlaps: last insert wins):
+ * VoxelCube::generateVoxelCube (geometry/VoxelCube.cuh:10-39: z faces red, x faces green, y faces blue) and
+ * VoxelSphere::generateVoxelSphere / generateCheckeredVoxelSphere (geometry/VoxelSphere.cuh:10-66, uint32 colour ramp). */
+int vrm_scene_generate_cube(vrm_scene* scene, int32_t x, int32_t y, int32_t z, int32_t half_width, uint64_t* n_out);
+int vrm_scene_generate_sphere(vrm_scene* scene, uint32_t x, uint32_t y, uint32_t z, uint32_t radius, int checkered, uint64_t* n_out);
 
 /* Build the chosen structure ON THE GPU (radix sort -> last-wins dedupe -> region directory ->
  * VCS cluster tables or cuckoo insertion).  build_ms (nullable) receives the device time. */

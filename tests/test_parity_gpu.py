@@ -418,3 +418,34 @@ def test_region_face_pingpong_and_tie_fast_forwards_are_bit_exact():
         if algo == "original":
             assert st["crawl_skipped"] > 0.9 * st["exist_checks"] > 250_000
     s.close()
+
+
+@pytest.mark.parametrize("storage", ["vcs", "hashtable"])
+def test_gpu_reference_generators_match_host_in_insertion_order(storage):
+    """vrm_scene_generate_cube / _sphere = the reference's VoxelCube / VoxelSphere generators (scenes.hollow_cube / sphere_shell,
+    which tests/test_scenes.py pins to the reference's functions).  The shapes overlap each other and a cube's faces overlap on
+    its edges, so the built scenes only agree if the GPU generators also reproduce the INSERTION ORDER (last insert wins)."""
+    parts = [("sphere", (40, 40, 40, 20, False)), ("cube", (44, 36, 52, 14)), ("sphere", (50, 44, 40, 17, True)), ("cube", (40, 40, 40, 9)),
+             ("cube", (-30, 5, -70, 6)), ("sphere", (120, 70, 64, 30, True))]
+    host, dev = api.VoxelScene(0), api.VoxelScene(0)
+    total = 0
+    for kind, args in parts:
+        xyz, rgb = scenes.hollow_cube(*args) if kind == "cube" else scenes.sphere_shell(*args[:4], checkered=args[4])
+        host.add_voxels(xyz, rgb)
+        n = dev.generate_cube(*args) if kind == "cube" else dev.generate_sphere(*args)
+        assert n == xyz.shape[0], (kind, args)
+        total += n
+    host.generate_voxel_scene(storage)
+    dev.generate_voxel_scene(storage)
+    ih, idv = host.info(), dev.info()
+    for k in ("diameter", "min_coord", "filled", "unique_voxels"):
+        assert ih[k] == idv[k], k
+    assert ih["unique_voxels"] < total          # the overlaps are real
+    allxyz = np.concatenate([(scenes.hollow_cube(*a) if k == "cube" else scenes.sphere_shell(*a[:4], checkered=a[4]))[0] for k, a in parts])
+    q = lookup_queries(allxyz, 20000, seed=9)
+    a, b = host.lookup(q), dev.lookup(q)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    with pytest.raises(api.VrmError):
+        api.VoxelScene(0).generate_sphere(5, 40, 40, 20)          # centre closer to the origin than the radius: the reference's unsigned bounds wrap
+    host.close()
+    dev.close()

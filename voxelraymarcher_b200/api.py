@@ -31,7 +31,7 @@ EMPTY = 1 << 30                                # EMPTY_KEY / EMPTY_VAL
 EXPORTS = [
     "vrm_error_string", "vrm_last_error", "vrm_device_available", "vrm_device_count", "vrm_device_name", "vrm_scene_create", "vrm_scene_destroy",
     "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
-    "vrm_scene_generate_terrain", "vrm_scene_generate_sparse_shells",
+    "vrm_scene_generate_terrain", "vrm_scene_generate_sparse_shells", "vrm_scene_generate_cube", "vrm_scene_generate_sphere",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_render_views", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
     "vrm_set_l2_persistence", "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
@@ -70,6 +70,8 @@ def load_library():
         "vrm_scene_add_voxels_device": (ci, [vp, vp, vp, u64]),
         "vrm_scene_generate_terrain": (ci, [vp, u32, u32, u32, C.POINTER(u64)]),
         "vrm_scene_generate_sparse_shells": (ci, [vp, u32, u32, u32, u32, C.POINTER(u64)]),
+        "vrm_scene_generate_cube": (ci, [vp, i32, i32, i32, i32, C.POINTER(u64)]),
+        "vrm_scene_generate_sphere": (ci, [vp, u32, u32, u32, u32, ci, C.POINTER(u64)]),
         "vrm_scene_build": (ci, [vp, ci, C.POINTER(f32)]),
         "vrm_scene_info": (ci, [vp, C.POINTER(u32), C.POINTER(i32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
         "vrm_set_lighting": (ci, [vp, vp, vp, vp, ci, ci]),
@@ -205,6 +207,18 @@ class VoxelScene:
         """``scenes.sparse_shells(size, cell, seed, fill_pct)`` generated on the GPU straight into the staging list."""
         n = C.c_uint64()
         self._check(self.lib.vrm_scene_generate_sparse_shells(self.h, size, cell, seed, fill_pct, C.byref(n)), "vrm_scene_generate_sparse_shells")
+        return int(n.value)
+
+    def generate_cube(self, x: int, y: int, z: int, half_width: int) -> int:
+        """``VoxelCube::generateVoxelCube`` (= ``scenes.hollow_cube``) on the GPU, in the reference's insertion order."""
+        n = C.c_uint64()
+        self._check(self.lib.vrm_scene_generate_cube(self.h, x, y, z, half_width, C.byref(n)), "vrm_scene_generate_cube")
+        return int(n.value)
+
+    def generate_sphere(self, x: int, y: int, z: int, radius: int, checkered: bool = False) -> int:
+        """``VoxelSphere::generate[Checkered]VoxelSphere`` (= ``scenes.sphere_shell``) on the GPU, in the reference's insertion order."""
+        n = C.c_uint64()
+        self._check(self.lib.vrm_scene_generate_sphere(self.h, x, y, z, radius, int(checkered), C.byref(n)), "vrm_scene_generate_sphere")
         return int(n.value)
 
     def generate_voxel_scene(self, storage_type):

@@ -141,6 +141,62 @@ __global__ void shell_fill_kernel(uint32_t n, uint32_t cellSize, uint32_t seed, 
 	}
 }
 
+// The reference's own (host-loop) generators, geometry/VoxelCube.cuh:10-39 and VoxelSphere.cuh:10-66, as index -> voxel maps
+// in the reference's INSERTION ORDER (faces of a cube overlap on its edges and shapes may overlap each other: the last
+// insert wins, so the order inside the staging chunk is part of the result).
+__global__ void cube_kernel(int xp, int yp, int zp, int hw, int32_t* __restrict__ xyz, uint32_t* __restrict__ rgb)
+{
+	const uint64_t w = 2ull * (uint64_t)hw, perGroup = 2ull * w * w;
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= 3ull * perGroup) return;
+	const int group = (int)(i / perGroup);           // 0: the two z faces (red), 1: x faces (green), 2: y faces (blue)
+	const uint64_t j = i % perGroup, pair = j / 2;
+	const bool second = (j & 1ull) != 0;
+	const int a = (int)(pair / w) - hw, b = (int)(pair % w) - hw;  // outer / inner loop variable
+	int x, y, z;
+	uint32_t colour;
+	if (group == 0) { x = xp + a; y = yp + b; z = zp + (second ? -hw : hw); colour = 0xFF0000u; }
+	else if (group == 1) { x = xp + (second ? hw : -hw); y = yp + a; z = zp + b; colour = 0x00FF00u; }
+	else { x = xp + a; y = yp + (second ? hw : -hw); z = zp + b; colour = 0x0000FFu; }
+	xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z;
+	rgb[i] = colour;
+}
+
+// candidate index (x-major, then y, then z) -> lattice point of the shell's bounding cube; all arithmetic uint32 as in the reference
+__device__ inline bool sphere_point(uint64_t idx, uint32_t xp, uint32_t yp, uint32_t zp, uint32_t r, uint32_t step, uint32_t& x, uint32_t& y, uint32_t& z)
+{
+	const uint32_t n = 2u * r;
+	const uint32_t ix = (uint32_t)(idx / ((uint64_t)n * n)), iy = (uint32_t)((idx / n) % n), iz = (uint32_t)(idx % n);
+	x = xp - r + ix * step; y = yp - r + iy; z = zp - r + iz;
+	const uint32_t d2 = (x - xp) * (x - xp) + (y - yp) * (y - yp) + (z - zp) * (z - zp);
+	return d2 < r * r && d2 > (r - 1u) * (r - 1u);
+}
+
+__global__ void sphere_flag_kernel(uint32_t xp, uint32_t yp, uint32_t zp, uint32_t r, uint32_t step, uint64_t candidates, uint32_t* __restrict__ flags)
+{
+	const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (idx >= candidates) return;
+	uint32_t x, y, z;
+	flags[idx] = sphere_point(idx, xp, yp, zp, r, step, x, y, z) ? 1u : 0u;
+}
+
+__global__ void sphere_fill_kernel(uint32_t xp, uint32_t yp, uint32_t zp, uint32_t r, uint32_t step, uint64_t candidates, const uint32_t* __restrict__ pos,
+                                   int32_t* __restrict__ xyz, uint32_t* __restrict__ rgb)
+{
+	const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (idx >= candidates) return;
+	uint32_t x, y, z;
+	if (!sphere_point(idx, xp, yp, zp, r, step, x, y, z)) return;
+	const uint32_t xMin = xp - r, xMax = xp + r, yMin = yp - r, yMax = yp + r, zMin = zp - r;
+	// the reference's colour ramp, quirks included: green measures y from xMin and the blue divisor is xMax - zMin
+	const uint32_t red = 50u + (x - xMin) * (200u / (xMax - xMin));
+	const uint32_t green = 50u + (y - xMin) * (200u / (yMax - yMin));
+	const uint32_t blue = 50u + (z - zMin) * (200u / (xMax - zMin));
+	const uint64_t o = pos[idx];
+	xyz[3 * o] = (int32_t)x; xyz[3 * o + 1] = (int32_t)y; xyz[3 * o + 2] = (int32_t)z;
+	rgb[o] = (min(red, 255u) << 16) | (min(green, 255u) << 8) | min(blue, 255u);
+}
+
 struct Buf
 {
 	void* p = nullptr;
@@ -208,6 +264,55 @@ int vrm_scene_generate_terrain(vrm_scene* s, uint32_t size, uint32_t seed, uint3
 	cudaError_t e = cudaGetLastError();
 	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
 	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_terrain"); }
+	s->chunks.push_back(c);
+	s->nStaged += total;
+	if (n_out) *n_out = total;
+	return VRM_OK;
+}
+
+int vrm_scene_generate_cube(vrm_scene* s, int32_t x, int32_t y, int32_t z, int32_t half_width, uint64_t* n_out)
+{
+	int rc = check_generate(s);
+	if (rc) return rc;
+	if (half_width < 1 || half_width > 4096) { s->lastError = "cube half width must be in [1, 4096]"; return VRM_ERR_INVALID; }
+	const uint64_t w = 2ull * (uint64_t)half_width, total = 6ull * w * w;
+	VoxelChunk c;
+	rc = stage_chunk(s, total, &c);
+	if (rc) return rc;
+	cube_kernel<<<grid_for(total), kThreads, 0, s->stream>>>(x, y, z, half_width, c.d_xyz, c.d_rgb);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_cube"); }
+	s->chunks.push_back(c);
+	s->nStaged += total;
+	if (n_out) *n_out = total;
+	return VRM_OK;
+}
+
+int vrm_scene_generate_sphere(vrm_scene* s, uint32_t x, uint32_t y, uint32_t z, uint32_t radius, int checkered, uint64_t* n_out)
+{
+	int rc = check_generate(s);
+	if (rc) return rc;
+	// the reference's unsigned loop bounds need pos >= radius; its colour ramp divides by 2 * radius and by x + radius - (z - radius)
+	if (radius < 2 || radius > 256 || x < radius || y < radius || z < radius || x > (1u << 22) || y > (1u << 22) || z > (1u << 22) || x + radius == z - radius)
+	{ s->lastError = "sphere: need 2 <= radius <= 256, every centre coordinate >= radius, x + radius != z - radius"; return VRM_ERR_INVALID; }
+	const uint32_t step = checkered ? 2u : 1u;
+	const uint64_t n = 2ull * radius, nx = (n + step - 1) / step, candidates = nx * n * n;
+	Buf flags, pos;
+	VRM_CUDA(s, cudaMalloc(&flags.p, candidates * 4));
+	VRM_CUDA(s, cudaMalloc(&pos.p, candidates * 4));
+	sphere_flag_kernel<<<grid_for(candidates), kThreads, 0, s->stream>>>(x, y, z, radius, step, candidates, flags.as<uint32_t>());
+	uint64_t total = 0;
+	rc = scan_counts(s, flags.as<uint32_t>(), pos.as<uint32_t>(), candidates, &total);
+	if (rc) return rc;
+	if (total == 0) { if (n_out) *n_out = 0; return VRM_OK; }
+	VoxelChunk c;
+	rc = stage_chunk(s, total, &c);
+	if (rc) return rc;
+	sphere_fill_kernel<<<grid_for(candidates), kThreads, 0, s->stream>>>(x, y, z, radius, step, candidates, pos.as<uint32_t>(), c.d_xyz, c.d_rgb);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_sphere"); }
 	s->chunks.push_back(c);
 	s->nStaged += total;
 	if (n_out) *n_out = total;
