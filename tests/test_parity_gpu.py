@@ -449,3 +449,21 @@ def test_gpu_reference_generators_match_host_in_insertion_order(storage):
         api.VoxelScene(0).generate_sphere(5, 40, 40, 20)          # centre closer to the origin than the radius: the reference's unsigned bounds wrap
     host.close()
     dev.close()
+
+
+def test_full_defer_queue_falls_back_to_crawling(monkeypatch):
+    """Rays that cannot be parked (queue of 3 slots, 12 ping-pong rays) crawl on in their kernel like the reference: same
+    colours, hit voxels and counters, just slower."""
+    from tests.test_hostsim import pingpong_scene_and_rays
+    monkeypatch.setenv("VRM_DEFER_CAPACITY", "3")
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    xyz, rgb, rays = pingpong_scene_and_rays()
+    s, ref = build_product(xyz, rgb, "vcs"), build_oracle(kind, xyz, rgb, "vcs")
+    s.set_statistics(True)
+    got, want = s.trace_rays(rays, "longestaxis", want_hits=True), ref.trace_rays(rays, "longestaxis", want_counters=True)
+    st = s.get_statistics()
+    assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"])
+    assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3])
+    assert 0 < st["crawl_skipped"] < 0.6 * st["exist_checks"]      # three rays were fast-forwarded, nine crawled
+    s.close()

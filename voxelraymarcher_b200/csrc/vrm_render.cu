@@ -7,6 +7,8 @@
 // kernels with virtual storage dispatch (the specialisation the reference's own dead OptimizedFunctions.cuh aimed at).
 // Compile with -fmad=false as a second line of defence; the core already spells every float op with *_rn intrinsics.
 #include "vrm_internal.h"
+
+#include <cstdlib>
 #include "vrm_flat.cuh"
 #include "../../include/vrm_b200.h"
 
@@ -467,7 +469,7 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 	a.defer = nullptr;
 }
 
-constexpr unsigned int kDeferCapacity = 16384;  // parked rays per launch (a 4K frame of the 2048^3 orbit parks a few dozen)
+constexpr unsigned int kDeferCapacity = 16384;  // parked rays per launch (a 4K frame of the 2048^3 orbit parks a few dozen); VRM_DEFER_CAPACITY overrides (tests)
 
 // The queue exists only for VCS + longest axis (the one combination that can ping-pong): reset its counter before the launch.
 template <int ST, int ALGO> void* prepare_defer_queue(vrm_scene* s)
@@ -477,9 +479,11 @@ template <int ST, int ALGO> void* prepare_defer_queue(vrm_scene* s)
 	static_assert(sizeof(Rec) == sizeof(typename FlatRay<ST, ALGO, true>::Deferred), "one queue layout for both statistics modes");
 	if (!s->d_defer)
 	{
-		const size_t bytes = sizeof(DeferHeader) + (size_t)kDeferCapacity * sizeof(Rec);
+		unsigned int capacity = kDeferCapacity;
+		if (const char* env = getenv("VRM_DEFER_CAPACITY")) { const long v = atol(env); if (v >= 1 && v <= (1l << 20)) capacity = (unsigned int)v; }
+		const size_t bytes = sizeof(DeferHeader) + (size_t)capacity * sizeof(Rec);
 		if (cudaMalloc(&s->d_defer, bytes) != cudaSuccess) { cudaGetLastError(); s->d_defer = nullptr; return nullptr; }  // no queue: such rays crawl like the reference
-		const DeferHeader h = {0u, kDeferCapacity, {0u, 0u}};
+		const DeferHeader h = {0u, capacity, {0u, 0u}};
 		cudaMemcpyAsync(s->d_defer, &h, sizeof(h), cudaMemcpyHostToDevice, s->stream);
 		cudaStreamSynchronize(s->stream);
 	}
