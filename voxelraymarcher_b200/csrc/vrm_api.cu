@@ -36,7 +36,7 @@ void vrm_apply_l2_window(vrm_scene* s)
 		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
 		void* base = s->storage == VRM_STORAGE_VCS ? static_cast<void*>(s->d_headers) : static_cast<void*>(s->d_slots);
 		size_t bytes = s->storage == VRM_STORAGE_VCS ? (size_t)s->filled * 512 * 16 * sizeof(uint2) : 0;
-		if (s->storage == VRM_STORAGE_HASHTABLE) bytes = s->bytes - (size_t)s->filled * sizeof(vrm::HashRegionDesc) - (size_t)s->diameter * s->diameter * s->diameter * 4;
+		if (s->storage == VRM_STORAGE_HASHTABLE) bytes = s->bytes - (size_t)s->filled * (sizeof(vrm::HashRegionDesc) + 64) - (size_t)s->diameter * s->diameter * s->diameter * 4;
 		if (base && bytes && maxPersist > 0 && maxWindow > 0)
 		{
 			const size_t carve = (size_t)maxPersist * 3 / 4;

@@ -309,6 +309,18 @@ __global__ void vcs_flag_clusters_kernel(uint2* __restrict__ headers, const uint
 	}
 }
 
+// Hash storage: the same 512-bit cluster-occupancy mask per region, used as a NEGATIVE FILTER in front of the two probes
+// (vrm_core.cuh lookup_voxel): a voxel of a cluster without voxels cannot be in the table.
+__global__ void cluster_mask_kernel(const unsigned long long* __restrict__ ukeys, const uint32_t* __restrict__ regionOf, uint64_t u, uint32_t* __restrict__ clusterMask)
+{
+	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (j >= u) return;
+	unsigned long long k = ukeys[j];
+	if (j != 0 && (ukeys[j - 1] >> 9) == (k >> 9)) return;  // one thread per (region, cluster): the sorted keys keep a cluster's voxels together
+	uint32_t cid = (uint32_t)(k >> 9) & 511u;
+	atomicOr(clusterMask + (size_t)regionOf[j] * 16 + (cid >> 5), 1u << (cid & 31));
+}
+
 // ---- 6b. cuckoo hash table -------------------------------------------------------------------------------------
 __global__ void fill_slots_kernel(unsigned long long* __restrict__ slots, uint64_t n)
 {
@@ -531,6 +543,9 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 		}
 		if (totalSlots >= (1ull << 32)) { s->lastError = "hash table needs more than 2^32 slots"; return VRM_ERR_INVALID; }
 		DeviceBuf failed, retry;
+		if (clusterMask.alloc((size_t)numRegions * 16 * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "hash table allocation failed"; return VRM_ERR_NOMEM; }
+		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4, st));
+		if (unique) cluster_mask_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, regionOf, unique, clusterMask.as<uint32_t>());
 		if (hashDesc.alloc((size_t)numRegions * sizeof(HashRegionDesc)) != cudaSuccess || slots.alloc(totalSlots * 8) != cudaSuccess ||
 		    failed.alloc((size_t)numRegions * 4) != cudaSuccess || retry.alloc((size_t)numRegions * 4) != cudaSuccess)
 		{ cudaGetLastError(); s->lastError = "hash table allocation failed"; return VRM_ERR_NOMEM; }
@@ -561,7 +576,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 			}
 			VRM_CUDA(s, cudaGetLastError());
 		}
-		bytes += (size_t)numRegions * sizeof(HashRegionDesc) + totalSlots * 8;
+		bytes += (size_t)numRegions * sizeof(HashRegionDesc) + totalSlots * 8 + (size_t)numRegions * 64;
 	}
 	trace.mark(st, storageType == VRM_STORAGE_VCS ? "vcs tables" : "cuckoo insertion");
 	VRM_CUDA(s, cudaEventRecord(s->ev1, st));
@@ -579,6 +594,7 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 	else
 	{
 		s->d_hashDesc = static_cast<HashRegionDesc*>(hashDesc.release());
+		s->d_clusterMask = static_cast<uint32_t*>(clusterMask.release());
 		s->d_slots = static_cast<unsigned long long*>(slots.release());
 	}
 	s->storage = storageType;

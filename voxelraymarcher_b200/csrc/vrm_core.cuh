@@ -281,12 +281,25 @@ template <class P, class T> VRM_HD void to_world(const P& p, const T* w, T* xyz)
 VRM_HD uint32_t hash_slot1(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 
+#ifndef VRM_HASH_CLUSTER_FILTER
+#define VRM_HASH_CLUSTER_FILTER 1
+#endif
+template <class T> VRM_HD T ldg(const T* p);
+// key = x << 12 | y << 6 | z (region-local, 6 bits each) -> cluster id (x/8) << 6 | (y/8) << 3 | z/8 -> bit of the region's mask
+VRM_HD bool hash_cluster_occupied(const uint32_t* clusterMask, uint32_t ri, uint32_t key)
+{
+	const uint32_t t = key >> 3;
+	const uint32_t cid = (t & 7u) | ((t >> 3) & 0x38u) | ((t >> 6) & 0x1C0u);
+	return ((ldg(clusterMask + (ri * 16u + (cid >> 5))) >> (cid & 31u)) & 1u) != 0u;
+}
+
 template <int ST> struct RegionRef;
 
 template <> struct RegionRef<kStorageHash>
 {
 	uint32_t base1, base2;  // first slot of table 1 / table 2 (32-bit indices into SceneView::slots: one IMAD.WIDE per probe)
 	uint32_t n, seed1, seed2;
+	uint32_t ri;            // dense region index (cluster-mask filter)
 };
 
 template <> struct RegionRef<kStorageVcs>
@@ -308,6 +321,7 @@ template <> VRM_HD RegionRef<kStorageHash> load_region<kStorageHash>(const Scene
 	r.base1 = d.slotBase;
 	r.base2 = d.slotBase + d.n;
 	r.n = d.n; r.seed1 = d.seed1; r.seed2 = d.seed2;
+	r.ri = (uint32_t)ri;
 	return r;
 }
 
@@ -381,11 +395,19 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 	{
 		const RegionRef<kStorageHash>& rh = r;
 		uint32_t key = ((uint32_t)g0 << (2 * p.cs(0))) | ((uint32_t)g1 << (2 * p.cs(1))) | ((uint32_t)g2 << (2 * p.cs(2)));
-		// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
-		unsigned long long e1 = ldg(c.sv.slots + (rh.base1 + hash_slot1(key, rh.seed1, rh.n)));
-		unsigned long long e2 = ldg(c.sv.slots + (rh.base2 + hash_slot2(key, rh.seed2, rh.n)));
-		if ((uint32_t)(e1 >> 32) == key) v = (uint32_t)e1;
-		else if ((uint32_t)(e2 >> 32) == key) v = (uint32_t)e2;
+#if VRM_HASH_CLUSTER_FILTER
+		// negative filter: a voxel whose 8^3 cluster holds no voxel at all cannot be in the table, and the 64-byte mask of the
+		// region answers that from L1 -- most lookups of a walk through open space never touch the (much larger) slot arrays.
+		// The traversal is untouched (the hash table's doesVoxelSpaceExist stays true: no cluster is ever skipped).
+		if (hash_cluster_occupied(c.sv.clusterMask, rh.ri, key))
+#endif
+		{
+			// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
+			unsigned long long e1 = ldg(c.sv.slots + (rh.base1 + hash_slot1(key, rh.seed1, rh.n)));
+			unsigned long long e2 = ldg(c.sv.slots + (rh.base2 + hash_slot2(key, rh.seed2, rh.n)));
+			if ((uint32_t)(e1 >> 32) == key) v = (uint32_t)e1;
+			else if ((uint32_t)(e2 >> 32) == key) v = (uint32_t)e2;
+		}
 		if (STATS) c.st.nProbe2++;
 	}
 	else

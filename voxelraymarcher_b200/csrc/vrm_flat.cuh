@@ -387,11 +387,16 @@ struct FlatRay
 		if constexpr (ST == kStorageHash)
 		{
 			const uint32_t key = ((uint32_t)c0 << sh[0]) | ((uint32_t)c1 << sh[1]) | ((uint32_t)c2 << sh[2]);
-			// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
-			const unsigned long long e1 = ldg(c.sv.slots + (r.base1 + hash_slot1(key, r.seed1, r.n)));
-			const unsigned long long e2 = ldg(c.sv.slots + (r.base2 + hash_slot2(key, r.seed2, r.n)));
-			if ((uint32_t)(e1 >> 32) == key) col = (uint32_t)e1;
-			else if ((uint32_t)(e2 >> 32) == key) col = (uint32_t)e2;
+#if VRM_HASH_CLUSTER_FILTER
+			if (hash_cluster_occupied(c.sv.clusterMask, r.ri, key))  // negative filter, see lookup_voxel (vrm_core.cuh)
+#endif
+			{
+				// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
+				const unsigned long long e1 = ldg(c.sv.slots + (r.base1 + hash_slot1(key, r.seed1, r.n)));
+				const unsigned long long e2 = ldg(c.sv.slots + (r.base2 + hash_slot2(key, r.seed2, r.n)));
+				if ((uint32_t)(e1 >> 32) == key) col = (uint32_t)e1;
+				else if ((uint32_t)(e2 >> 32) == key) col = (uint32_t)e2;
+			}
 			if (STATS) { c.st.nExist++; c.st.nLookup++; c.st.nProbe2++; if (col != kEmpty) c.st.nLookupHit++; }
 			return true;
 		}
