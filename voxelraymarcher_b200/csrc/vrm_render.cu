@@ -2,7 +2,7 @@
 // rayMarchSceneJumpAxis (renderer/Renderer.cuh:1033-1063) and their launch (main/Main.cu:105-163).
 //
 // One thread per pixel; a warp owns an 8x4 pixel tile (coherent primary rays: neighbouring pixels walk the same
-// clusters, so their lookups share 128-byte lines), a 256-thread CTA owns a 32x8 block of pixels, blockIdx.z is the
+// clusters, so their lookups share 128-byte lines), a 128-thread CTA owns a 32x4 row of four tiles, blockIdx.z is the
 // view.  Storage type and algorithm are template parameters: four specialised kernels instead of the reference's two
 // kernels with virtual storage dispatch (the specialisation the reference's own dead OptimizedFunctions.cuh aimed at).
 // Compile with -fmad=false as a second line of defence; the core already spells every float op with *_rn intrinsics.
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 	const uint32_t x0 = blockIdx.x * kBlockW, y0 = a.yBase + blockIdx.y * kBlockH;
 	const uint32_t x = x0 + lx, y = y0 + ly;
 	const bool inside = x < a.W && y < a.yEnd;
-	// The CTA's 32x8 pixels are staged in shared memory and written as 8 rows of 96 contiguous bytes (24 words per row,
+	// The CTA's 32x4 pixels are staged in shared memory and written as 4 rows of 96 contiguous bytes (24 words per row,
 	// one STG.32 per thread) instead of three scattered byte stores per pixel (Renderer.cuh:1027-1030); this is also what makes
 	// writing the frame straight into pinned host memory (vrm_render) efficient.
 	__shared__ uint32_t staged[kBlockH][kBlockW * 3 / 4];
@@ -507,10 +507,10 @@ template <int ST, int ALGO, class Args> void launch_resume(vrm_scene* s, const A
 template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim3 grid)
 {
 	// Which form of the traversal runs is a measured choice per combination (512^3 terrain, 4K, B200):
-	// the per-lane state machine wins where cluster jumps nest inside the longest-axis loop (VCS + longest axis: 2.06 ms
-	// vs 2.87 ms nested); the nested loops win or tie elsewhere.  VRM_RENDER_MODE=0|1|2 forces one form for A/B runs.
+	// the per-lane state machine wins where cluster jumps nest inside the longest-axis loop (VCS + longest axis: 1.50 ms
+	// vs 2.9 ms nested); the nested loops win elsewhere (VCS + original 1.05 vs 1.16 ms, hash table 2.95 / 3.08 vs 3.45 / 3.94 ms).  VRM_RENDER_MODE=0|1|2 forces one form for A/B runs.
 	const int mode = s->renderMode >= 0 ? s->renderMode : ((ST == kStorageVcs && ALGO != kAlgoOriginal) ? 2 : 1);
-	if (mode == 1)  // nested form, one CTA per 32x8 pixels
+	if (mode == 1)  // nested form, one CTA per 32x4 pixels
 	{
 		if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
