@@ -129,6 +129,12 @@ int vrm_render_device(vrm_scene* scene, const float camera[VRM_CAMERA_FLOATS], c
 int vrm_render_views_device(vrm_scene* scene, const float* cameras, uint32_t n_views, const float translation[3],
                             uint32_t scale, int algorithm, uint32_t width, uint32_t height, uint8_t* d_rgb_out,
                             int32_t* d_hits_out);
+/* The same with the frames of consecutive views view_stride frame slots apart in the outputs (view v goes to slot v * view_stride):
+ * interleaved sharding of a view batch over GPUs -- rank r of N renders views r, r + N, ... with view_stride = N into the shared frame
+ * buffer starting at slot r -- balances views of unequal cost better than contiguous blocks. */
+int vrm_render_views_device_strided(vrm_scene* scene, const float* cameras, uint32_t n_views, const float translation[3],
+                                    uint32_t scale, int algorithm, uint32_t width, uint32_t height, uint8_t* d_rgb_out,
+                                    int32_t* d_hits_out, uint32_t view_stride);
 
 /* Streaming multi-view render into HOST frames (n_views x height x width x 3, view-major): the camera orbit of
  * BASELINE.json configs[3] as one call (the reference renders exactly one frame per process, main/Main.cu:105-163).

@@ -14,6 +14,17 @@ from tests.common import scenes
 from voxelraymarcher_b200 import api, multigpu
 
 
+def test_shard_views_interleaved_partitions_exactly():
+    for n in (0, 1, 5, 64, 67):
+        for world in (1, 2, 3, 8):
+            seen = sorted(v for r in range(world) for v in multigpu.shard_views_interleaved(n, world, r))
+            assert seen == list(range(n))
+            sizes = [len(multigpu.shard_views_interleaved(n, world, r)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        multigpu.shard_views_interleaved(4, 2, 2)
+
+
 def test_shard_views_partitions_exactly():
     for n in (0, 1, 7, 64, 65):
         for world in (1, 2, 3, 8):

@@ -467,3 +467,25 @@ def test_full_defer_queue_falls_back_to_crawling(monkeypatch):
     assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3])
     assert 0 < st["crawl_skipped"] < 0.6 * st["exist_checks"]      # three rays were fast-forwarded, nine crawled
     s.close()
+
+
+def test_strided_view_batch_fills_interleaved_slots(probe):
+    """vrm_render_views_device_strided: two "ranks" render the odd and the even views of a 5-view batch into one shared frame buffer
+    (view_stride 2, starting at their own slot); the buffer must equal the single-frame renders, hit maps included."""
+    import torch
+    xyz, rgb = probe
+    w, h = 160, 90
+    s = build_product(xyz, rgb, "vcs")
+    cams = [api.Camera((6.0 + 0.7 * v, 2.0 + 0.2 * v, 6.0 - 0.4 * v), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h)) for v in range(5)]
+    for algo in ("longestaxis", "original"):
+        frames = torch.zeros((5, h, w, 3), dtype=torch.uint8, device="cuda:0")
+        hits = torch.zeros((5, h, w, 4), dtype=torch.int32, device="cuda:0")
+        for rank in range(2):
+            mine = range(rank, 5, 2)
+            s.render_views_device(w, h, algo, [cams[i] for i in mine], frames[rank].data_ptr(), hits[rank].data_ptr(), scale=8, view_stride=2)
+        s.synchronize()
+        for v in range(5):
+            one = s.render(w, h, algo, cams[v], scale=8, want_hits=True)
+            assert np.array_equal(frames[v].cpu().numpy(), one["rgb"]), (algo, v)
+            assert np.array_equal(hits[v].cpu().numpy(), one["hits"]), (algo, v)
+    s.close()

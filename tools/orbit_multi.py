@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--algo", default="longestaxis")
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--interleave", action="store_true", help="deal the views out round-robin (view_stride = world size) instead of contiguous blocks")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -38,7 +39,8 @@ def main():
         ang = 2.0 * np.pi * (v + 0.37) / views
         r, el, c = 1.5 * size / 2, np.deg2rad(20.0), size / 2
         cams.append(api.Camera((float(c + r * np.cos(el) * np.cos(ang)), float(c + r * np.sin(el)), float(c + r * np.cos(el) * np.sin(ang))), (c, c, c), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h)))
-    mine = multigpu.shard_views(views, world, rank)
+    mine = multigpu.shard_views_interleaved(views, world, rank) if a.interleave else multigpu.shard_views(views, world, rank)
+    stride = world if a.interleave else 1
     peer = multigpu.PeerFrameBuffer(views, w, h, local) if world > 1 else None
     local_frames = torch.zeros((len(mine), h, w, 3), dtype=torch.uint8, device=dev) if peer is None else None
     out_ptr = peer.ptr_for(mine.start) if peer is not None else local_frames.data_ptr()
@@ -50,7 +52,7 @@ def main():
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        s.render_views_device(w, h, a.algo, [cams[i] for i in mine], out_ptr)
+        s.render_views_device(w, h, a.algo, [cams[i] for i in mine], out_ptr, view_stride=stride if peer is not None else 1)
         if world > 1:
             dist.all_reduce(token)
         e1.record(stream)
@@ -69,11 +71,11 @@ def main():
         dist.barrier()
         if rank == 0:
             full = peer.to_tensor()
-            ok = bool(torch.equal(full[mine.start:mine.stop], check))
+            ok = bool(torch.equal(full[mine.start:mine.stop:mine.step], check))
     if rank == 0:
         ms = float(np.median(times))
         print(json.dumps(dict(config="4: 2048^3 sparse shells, 64-view orbit 1920x1080", algo=a.algo, n_gpus=world, views=views, voxels=n, build_ms=build_ms,
-                              ms_orbit=ms, ms_per_frame=ms / views, mrays_per_s=w * h * views / ms / 1e3, rank0_block_verified=ok)), flush=True)
+                              sharding="interleaved" if a.interleave else "contiguous", ms_orbit=ms, ms_per_frame=ms / views, mrays_per_s=w * h * views / ms / 1e3, rank0_block_verified=ok)), flush=True)
     if world > 1:
         dist.barrier()
         if peer is not None:

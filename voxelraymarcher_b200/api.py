@@ -33,7 +33,7 @@ EXPORTS = [
     "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
     "vrm_scene_generate_terrain", "vrm_scene_generate_sparse_shells", "vrm_scene_generate_cube", "vrm_scene_generate_sphere",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
-    "vrm_render_device", "vrm_render_views_device", "vrm_render_views", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
+    "vrm_render_device", "vrm_render_views_device", "vrm_render_views_device_strided", "vrm_render_views", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
     "vrm_set_l2_persistence", "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
 ]
 
@@ -80,6 +80,7 @@ def load_library():
         "vrm_render": (ci, [vp, vp, vp, u32, ci, u32, u32, vp, vp, C.POINTER(f32)]),
         "vrm_render_device": (ci, [vp, vp, vp, u32, ci, u32, u32, vp, vp]),
         "vrm_render_views_device": (ci, [vp, vp, u32, vp, u32, ci, u32, u32, vp, vp]),
+        "vrm_render_views_device_strided": (ci, [vp, vp, u32, vp, u32, ci, u32, u32, vp, vp, u32]),
         "vrm_render_views": (ci, [vp, vp, u32, vp, u32, ci, u32, u32, vp, C.POINTER(f32)]),
         "vrm_trace_rays": (ci, [vp, vp, u64, vp, u32, ci, vp, vp, C.POINTER(f32)]),
         "vrm_trace_rays_device": (ci, [vp, vp, u64, vp, u32, ci, vp, vp]),
@@ -280,10 +281,12 @@ class VoxelScene:
                                                C.c_void_p(d_rgb_ptr), C.c_void_p(d_hits_ptr or 0)), "vrm_render_device")
 
     def render_views_device(self, width, height, algorithm, cameras, d_rgb_ptr: int, d_hits_ptr: int | None = None, scale=1,
-                            translation=(0.0, 0.0, 0.0)):
+                            translation=(0.0, 0.0, 0.0), view_stride: int = 1):
+        """All ``cameras`` in one launch; view ``v`` goes to frame slot ``v * view_stride`` of the outputs."""
         cams = np.ascontiguousarray(np.stack([self._cam(c) for c in cameras]), np.float32)
-        self._check(self.lib.vrm_render_views_device(self.h, _ptr(cams), cams.shape[0], _ptr(_f3(translation)), scale, self._algo(algorithm),
-                                                     width, height, C.c_void_p(d_rgb_ptr), C.c_void_p(d_hits_ptr or 0)), "vrm_render_views_device")
+        self._check(self.lib.vrm_render_views_device_strided(self.h, _ptr(cams), cams.shape[0], _ptr(_f3(translation)), scale, self._algo(algorithm),
+                                                             width, height, C.c_void_p(d_rgb_ptr), C.c_void_p(d_hits_ptr or 0), int(view_stride)),
+                    "vrm_render_views_device_strided")
 
     def render_views(self, width, height, algorithm, cameras, scale=1, translation=(0.0, 0.0, 0.0), rgb_out=None):
         """A batch of views (camera orbit) into host frames ``[n, H, W, 3]``; ``rgb_out`` may be a pinned buffer (written directly

@@ -296,16 +296,22 @@ int vrm_set_lighting(vrm_scene* s, const float direction[3], const float colour[
 	return VRM_OK;
 }
 
-int vrm_render_views_device(vrm_scene* s, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale, int algorithm,
-                            uint32_t width, uint32_t height, uint8_t* d_rgb_out, int32_t* d_hits_out)
+int vrm_render_views_device_strided(vrm_scene* s, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale, int algorithm,
+                                    uint32_t width, uint32_t height, uint8_t* d_rgb_out, int32_t* d_hits_out, uint32_t view_stride)
 {
 	int rc = check_render_args(s, cameras, translation, algorithm, width, height);
 	if (rc) return rc;
-	if (!d_rgb_out || n_views == 0 || n_views > 65535) { s->lastError = "invalid render arguments"; return VRM_ERR_INVALID; }
+	if (!d_rgb_out || n_views == 0 || n_views > 65535 || view_stride == 0) { s->lastError = "invalid render arguments"; return VRM_ERR_INVALID; }
 	VRM_CUDA(s, cudaSetDevice(s->device));
 	rc = upload_cameras(s, cameras, n_views);
 	if (rc) return rc;
-	return vrm_launch_render(s, s->d_cams, n_views, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out);
+	return vrm_launch_render(s, s->d_cams, n_views, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out, 0, 0xFFFFFFFFu, view_stride);
+}
+
+int vrm_render_views_device(vrm_scene* s, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale, int algorithm,
+                            uint32_t width, uint32_t height, uint8_t* d_rgb_out, int32_t* d_hits_out)
+{
+	return vrm_render_views_device_strided(s, cameras, n_views, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out, 1);
 }
 
 int vrm_render_device(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float translation[3], uint32_t scale, int algorithm,

@@ -99,7 +99,7 @@ void vrm_apply_l2_window(vrm_scene* s);
 
 // vrm_render.cu
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
-                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase = 0, uint32_t yEnd = 0xFFFFFFFFu);
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase = 0, uint32_t yEnd = 0xFFFFFFFFu, uint32_t viewStride = 1);
 int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float* translation, uint32_t scale, int algorithm,
                      uint32_t* d_colour, int32_t* d_hits);
 int vrm_launch_lookup(vrm_scene* s, const int32_t* d_xyz, uint64_t n, uint32_t* d_out, uint8_t* d_exists);

@@ -55,6 +55,7 @@ struct RenderArgs
 	float scale;
 	const float* cams;  // nViews x 15
 	uint32_t W, H;
+	size_t viewPixels;     // pixel slots between the outputs of consecutive views (W * H, or a multiple of it for interleaved view sharding)
 	float invW, invH;      // RN(1 / W), RN(1 / H) (host): exact division by a constant in primary_ray_flat
 	uint32_t rowWordsOk;   // 1 when every 32-pixel row segment starts on a 4-byte boundary (W * 3 % 4 == 0 and an aligned base)
 	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
@@ -174,14 +175,14 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 			primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
 			if (a.hits)
 			{
-				c.hitOut = a.hits + 4 * (((size_t)blockIdx.z * a.H + y) * a.W + x);
+				c.hitOut = a.hits + 4 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x);
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
 		}
 		c.deferQueue = a.defer;
 		int slot;
 		color = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, slot);
-		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (((size_t)blockIdx.z * a.H + y) * a.W + x), 0u);
+		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x), 0u);
 	}
 	else if (inside)
 	{
@@ -199,18 +200,18 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 			if (a.hits)
 			{
 				// the hit map slot is cleared here and filled at the hit site (record_hit_voxel)
-				c.hitOut = a.hits + 4 * (((size_t)blockIdx.z * a.H + y) * a.W + x);
+				c.hitOut = a.hits + 4 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x);
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
 			c.deferQueue = a.defer;
 			int slot;
 			color = march_scene_flat<ST, ALGO, STATS, kPpDefer>(c, o, d, a.scale, slot);
-			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (((size_t)blockIdx.z * a.H + y) * a.W + x), 0u);
+			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x), 0u);
 		}
 		else
 		{
 			color = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
-			if (a.hits) reinterpret_cast<int4*>(a.hits)[((size_t)blockIdx.z * a.H + y) * a.W + x] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
+			if (a.hits) reinterpret_cast<int4*>(a.hits)[(size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 		}
 	}
 	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		if (lane < kTileH * (kTileW * 3 / 4))
 		{
 			const uint32_t row = lane / (kTileW * 3 / 4), w = lane % (kTileW * 3 / 4);
-			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + (((size_t)blockIdx.z * a.H + ty0 + row) * a.W + tx0) * 3);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.viewPixels + (size_t)(ty0 + row) * a.W + tx0) * 3);
 			dst[w] = mine[row][w];
 		}
 	}
@@ -241,14 +242,14 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		if (threadIdx.x < kBlockH * (kBlockW * 3 / 4))
 		{
 			const uint32_t row = threadIdx.x / (kBlockW * 3 / 4), w = threadIdx.x % (kBlockW * 3 / 4);
-			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + (((size_t)blockIdx.z * a.H + y0 + row) * a.W + x0) * 3);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.viewPixels + (size_t)(y0 + row) * a.W + x0) * 3);
 			dst[w] = staged[row][w];
 		}
 	}
 #endif
 	else if (inside)
 	{
-		size_t p = ((size_t)blockIdx.z * a.H + y) * a.W + x;
+		size_t p = (size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x;
 		a.rgb[3 * p] = (uint8_t)(color >> 16);
 		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
 		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 						for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
 						float o[3], d[3];
 						primary_ray(camv, x, y, a.W, a.H, o, d);
-						pixel = ((size_t)view * a.H + y) * a.W + x;
+						pixel = (size_t)view * a.viewPixels + (size_t)y * a.W + x;
 						if (a.hits)
 						{
 							c.hitOut = a.hits + 4 * pixel;
@@ -562,7 +563,7 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 }  // namespace
 
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
-                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase, uint32_t yEnd)
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase, uint32_t yEnd, uint32_t viewStride)
 {
 	if (yEnd > H) yEnd = H;
 	vrm_apply_l2_window(s);
@@ -570,6 +571,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
 	a.invW = 1.0f / (float)W; a.invH = 1.0f / (float)H;
+	a.viewPixels = (size_t)W * H * (viewStride ? viewStride : 1u);
 	a.yBase = yBase; a.yEnd = yEnd;
 	a.rowWordsOk = ((W * 3u) % 4u == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 3u) == 0 && (((size_t)W * H * 3) % 4 == 0 || nViews == 1)) ? 1u : 0u;
 	a.queue = s->d_queue;

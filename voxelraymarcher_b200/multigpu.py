@@ -22,6 +22,15 @@ def shard_views(n_views: int, world_size: int, rank: int) -> range:
     return range(start, start + base + (1 if rank < extra else 0))
 
 
+def shard_views_interleaved(n_views: int, world_size: int, rank: int) -> range:
+    """Views ``rank, rank + world_size, ...``: neighbouring views of an orbit cost about the same, so dealing them out round-robin
+    balances the ranks better than contiguous blocks when the cost varies along the orbit.  With a shared frame buffer
+    (``PeerFrameBuffer``) a rank renders its views in one launch with ``view_stride = world_size`` starting at slot ``rank``."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world size")
+    return range(rank, n_views, world_size)
+
+
 def gather_frames(local_frames, n_views: int, group=None, dst: int = 0):
     """Gather per-rank frame blocks ``[n_local, H, W, 3]`` (uint8, same device on every rank) on ``dst``.
     Returns the full ``[n_views, H, W, 3]`` tensor on ``dst`` and ``None`` elsewhere.  Ranks may own different numbers
