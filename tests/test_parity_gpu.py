@@ -423,7 +423,7 @@ def test_region_face_pingpong_and_tie_fast_forwards_are_bit_exact():
 @pytest.mark.parametrize("storage", ["vcs", "hashtable"])
 def test_gpu_reference_generators_match_host_in_insertion_order(storage):
     """vrm_scene_generate_cube / _sphere = the reference's VoxelCube / VoxelSphere generators (scenes.hollow_cube / sphere_shell,
-    which tests/test_scenes.py pins to the reference's functions).  The shapes overlap each other and a cube's faces overlap on
+    which tests/test_oracle.py pins to the reference's functions).  The shapes overlap each other and a cube's faces overlap on
     its edges, so the built scenes only agree if the GPU generators also reproduce the INSERTION ORDER (last insert wins)."""
     parts = [("sphere", (40, 40, 40, 20, False)), ("cube", (44, 36, 52, 14)), ("sphere", (50, 44, 40, 17, True)), ("cube", (40, 40, 40, 9)),
              ("cube", (-30, 5, -70, 6)), ("sphere", (120, 70, 64, 30, True))]

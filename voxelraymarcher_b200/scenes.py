@@ -7,7 +7,7 @@ INSERTION ORDER -- the scene semantics are last-write-wins on duplicate coordina
 
 The cube / sphere generators restate the reference's own (unused by its ``main``) generators:
 VoxelRaymarcher/src/geometry/VoxelCube.cuh:10-39 and VoxelSphere.cuh:10-66, including their uint32 colour
-arithmetic; tests/test_scenes.py checks them voxel-for-voxel against the reference's functions.
+arithmetic; tests/test_oracle.py checks them against the reference's own functions (run through the host build of the reference).
 """
 from __future__ import annotations
 
