@@ -515,10 +515,14 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 		const size_t headerBytes = (size_t)numRegions * 512 * 16 * sizeof(uint2);
 		// 31-bit colour indices (the top bit of a header's index word is the cluster-exists flag), 32-bit header word indices
 		if (unique >= (1ull << 31) || (uint64_t)numRegions * 8192ull >= (1ull << 32)) { s->lastError = "scene too large for the VCS index widths"; return VRM_ERR_INVALID; }
-		if (headers.alloc(headerBytes) != cudaSuccess || clusterMask.alloc((size_t)numRegions * 16 * 4) != cudaSuccess)
+		// Zeroed guard space behind both arrays: the reference can test a voxel with a coordinate of exactly 64 (a ray rebased onto the
+		// far face of a region; undefined behaviour there, VoxelClusterStore.cuh:93-99 indexes past its 512-entry table) and the nested
+		// traversal then forms a cluster id of up to 575 -- for the LAST region that reads up to 64 clusters past the end.
+		const size_t headerGuard = 64 * 16 * sizeof(uint2), maskGuard = 64;
+		if (headers.alloc(headerBytes + headerGuard) != cudaSuccess || clusterMask.alloc((size_t)numRegions * 16 * 4 + maskGuard) != cudaSuccess)
 		{ cudaGetLastError(); s->lastError = "VCS allocation failed"; return VRM_ERR_NOMEM; }
-		VRM_CUDA(s, cudaMemsetAsync(headers.p, 0, headerBytes, st));
-		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4, st));
+		VRM_CUDA(s, cudaMemsetAsync(headers.p, 0, headerBytes + headerGuard, st));
+		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4 + maskGuard, st));
 		if (unique)
 			vcs_fill_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, regionOf, unique, headers.as<uint2>(), clusterMask.as<uint32_t>());
 		if (unique)
@@ -543,8 +547,8 @@ int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs)
 		}
 		if (totalSlots >= (1ull << 32)) { s->lastError = "hash table needs more than 2^32 slots"; return VRM_ERR_INVALID; }
 		DeviceBuf failed, retry;
-		if (clusterMask.alloc((size_t)numRegions * 16 * 4) != cudaSuccess) { cudaGetLastError(); s->lastError = "hash table allocation failed"; return VRM_ERR_NOMEM; }
-		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4, st));
+		if (clusterMask.alloc((size_t)numRegions * 16 * 4 + 64) != cudaSuccess) { cudaGetLastError(); s->lastError = "hash table allocation failed"; return VRM_ERR_NOMEM; }
+		VRM_CUDA(s, cudaMemsetAsync(clusterMask.p, 0, (size_t)numRegions * 16 * 4 + 64, st));
 		if (unique) cluster_mask_kernel<<<grid_for(unique), kThreads, 0, st>>>(ukeys, regionOf, unique, clusterMask.as<uint32_t>());
 		if (hashDesc.alloc((size_t)numRegions * sizeof(HashRegionDesc)) != cudaSuccess || slots.alloc(totalSlots * 8) != cudaSuccess ||
 		    failed.alloc((size_t)numRegions * 4) != cudaSuccess || retry.alloc((size_t)numRegions * 4) != cudaSuccess)
