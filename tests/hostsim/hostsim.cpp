@@ -133,6 +133,59 @@ extern "C" {
 void sim_set_flat(int flat) { gFlat = flat; }
 int sim_is_flat() { return gFlat; }
 
+// crawl_skip against the literal iterations it replaces: pseudo-random positions (many of them exactly on cluster faces, integers and
+// powers of two, or a few ulps away from them) and directions whose EPSILON steps range from "cannot move the coordinate" to
+// hundreds of ulps.  For every case in which crawl_skip skips M > 0 iterations: executing o <- RN(o + RN(EPSILON * d)) M times must
+// give the same bits, and every intermediate position must still truncate into the cluster cell that is being skipped.
+// Returns the number of failing cases; *skippedCases receives how many cases actually skipped something.
+uint64_t sim_check_crawl_skip(uint32_t seed, uint64_t count, uint64_t* skippedCases)
+{
+	uint64_t bad = 0, used = 0, st = seed * 0x9E3779B97F4A7C15ull + 12345;
+	auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (uint32_t)(st >> 20); };
+	auto unit = [&]() { return (float)(next() & 0xFFFFFF) / 16777216.0f; };
+	for (uint64_t n = 0; n < count; n++)
+	{
+		float o[3], d[3];
+		int v[3];
+		for (int i = 0; i < 3; i++)
+		{
+			const int cell = (int)(next() % 8u) * 8;
+			float y;
+			switch (next() % 6u)
+			{
+			case 0: y = (float)cell; break;                                            // on the lower cluster face
+			case 1: y = (float)(cell + (int)(next() % 8u)); break;                      // on an integer
+			case 2: y = (float)(1u << (next() % 6u)); break;                            // a power of two
+			case 3: y = bits_float(float_bits((float)(cell + 1 + (int)(next() % 7u))) + (next() % 5u) - 2u); break;  // a few ulps around an integer
+			default: y = (float)cell + 8.0f * unit(); break;
+			}
+			if (!(y >= 0.0f && y < 64.0f)) y = 1.5f;
+			o[i] = y;
+			v[i] = (int)y;
+			const float mag = (next() % 3u == 0u) ? 1.0f : ((next() % 2u) ? 0.05f : 0.004f);
+			d[i] = (unit() * 2.0f - 1.0f) * mag;
+			if (d[i] == 0.0f) d[i] = 0.001f;
+		}
+		const RayDir k = make_raydir(d[0], d[1], d[2]);
+		float p[3] = {o[0], o[1], o[2]};
+		const int m = crawl_skip(p, k, v[0], v[1], v[2]);
+		if (m <= 0) continue;
+		used++;
+		float q[3] = {o[0], o[1], o[2]};
+		bool ok = true;
+		for (int it = 0; it < m && ok; it++)
+			for (int i = 0; i < 3; i++)
+			{
+				q[i] = vadd(q[i], vmul(kEps, k.d[i]));
+				if (it + 1 < m && (((int)q[i]) & ~7) != (v[i] & ~7)) ok = false;
+			}
+		for (int i = 0; i < 3; i++) if (float_bits(q[i]) != float_bits(p[i])) ok = false;
+		if (!ok) bad++;
+	}
+	if (skippedCases) *skippedCases = used;
+	return bad;
+}
+
 // primary_ray_flat's image-plane divisions against IEEE division: every pixel coordinate of an image side of n pixels.
 // Returns the number of mismatches (0 expected).
 uint64_t sim_check_image_division(uint32_t n)
@@ -258,6 +311,10 @@ int sim_scene_build(void* h, int storageType)
 		s->hashDesc.push_back(d);
 		ri++;
 	}
+	// zeroed guard space, as in the product's builder: the reference can test a voxel with a coordinate of exactly 64 (undefined
+	// behaviour there) and the nested traversal then forms cluster ids of up to 575
+	s->headers.resize(s->headers.size() + 64 * 16, uint2{0, 0});
+	s->clusterMask.resize(s->clusterMask.size() + 16, 0u);
 	s->storage = storageType;
 	return 0;
 }

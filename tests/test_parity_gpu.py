@@ -489,3 +489,19 @@ def test_strided_view_batch_fills_interleaved_slots(probe):
             assert np.array_equal(frames[v].cpu().numpy(), one["rgb"]), (algo, v)
             assert np.array_equal(hits[v].cpu().numpy(), one["hits"]), (algo, v)
     s.close()
+
+
+@pytest.mark.parametrize("algo", ["original", "longestaxis"])
+def test_rays_starting_on_power_of_two_coordinates(algo):
+    """The crawl_skip regression of tests/test_hostsim.py (an axis on a cluster face at local 16.0 is not stuck) through the kernels."""
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    xyz, rgb = scenes.terrain(160, 77)
+    s, ref = build_product(xyz, rgb, "vcs"), build_oracle(kind, xyz, rgb, "vcs")
+    rays = scenes.random_rays(20000, (80.0, 150.0, 80.0), seed=101)
+    s.set_statistics(True)
+    got, want = s.trace_rays(rays, algo, want_hits=True), ref.trace_rays(rays, algo, want_counters=True)
+    st = s.get_statistics()
+    assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"])
+    assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3])
+    s.close()

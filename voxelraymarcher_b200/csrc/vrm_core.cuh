@@ -627,14 +627,22 @@ VRM_HD int crawl_skip(float* o, const float* dir, float thr, int v0, int v1, int
 		const int cell = v[i] & ~7;
 		uint32_t lo = float_bits((float)cell), hi = float_bits((float)(cell + 8));
 		const uint32_t blo = eb << 23, bhi = (eb + 1u) << 23;
+		// A step DOWN must land strictly above the binade's first float: the exact sum of a step that "lands on" the power of two
+		// can lie below it, where the floats are twice as dense, and then rounds to one of those instead (a differential run
+		// against the oracle found 32.0 vs 31.9999981)
 		if (lo < blo) lo = blo;
 		if (hi > bhi) hi = bhi;
 		if (yb < lo || yb >= hi) return 0;  // (int)o is not in the cell being skipped
+		if (lo == blo) lo = blo + 1u;       // lowest pattern a step down may land on
 		int m;
 		if (qi > 0) m = (int)((hi - 1u - yb) / (uint32_t)qi);
-		else if (qi < 0) m = (int)((yb - lo) / (uint32_t)(-qi));
+		else if (qi < 0) m = yb >= lo ? (int)((yb - lo) / (uint32_t)(-qi)) : 0;
 		else
 		{
+			// "does not move" must hold for the addition itself: from a power of two a negative c steps into the binade below, whose
+			// floats are twice as dense, so |c| between a quarter and half an ulp of y DOES move it (found by a differential run
+			// against the oracle: a ray starting on local coordinate 16.0)
+			if (vadd(y, c) != y) return 0;
 			m = 0x7FFFFFFF;
 			if ((float)cluster_edge(dir[i], v[i]) == y) stuck = true;  // this axis sits on its cluster face and cannot move: t_i = 0
 		}

@@ -79,7 +79,10 @@ constexpr int32_t kRiPending = -3;       // FlatRay::ri: the ray has left its re
 //              the hot kernels: compiled into them -- even as a never-taken branch -- it cost 30 % of their speed.
 //   kPpInline  fast-forward in place (resume kernel, host harness)
 constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
-constexpr int kPpDefault = kPpInline;  // single-ray callers (host harness); the kernels name their policy
+#ifndef VRM_PP_DEFAULT
+#define VRM_PP_DEFAULT 2
+#endif
+constexpr int kPpDefault = VRM_PP_DEFAULT;  // single-ray callers (host harness; 0 there = crawl like the reference); the kernels name their policy
 
 struct DeferHeader
 {
@@ -690,7 +693,8 @@ struct FlatRay
 		if (lo < blo) lo = blo;
 		if (hi > bhi) hi = bhi;
 		if (xb < lo || xb >= hi) return false;
-		const uint32_t room = q > 0 ? (hi - 1u - xb) / (uint32_t)q : (xb - lo) / (uint32_t)(-q);  // advances that keep o[0] inside
+		if (lo == blo) lo = blo + 1u;  // a step down must land strictly above the binade's first float (see crawl_skip)
+		const uint32_t room = q > 0 ? (hi - 1u - xb) / (uint32_t)q : (xb >= lo ? (xb - lo) / (uint32_t)(-q) : 0u);  // advances that keep o[0] inside
 		const uint32_t cycles = room / 2u;  // whole cycles that keep o[0] inside
 		if (cycles < 4u) return false;
 		const FlatRay start = *this;
