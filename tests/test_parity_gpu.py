@@ -505,3 +505,23 @@ def test_rays_starting_on_power_of_two_coordinates(algo):
     assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"])
     assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3])
     s.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("algo", ["original", "longestaxis"])
+def test_trace_fuzz_from_grid_aligned_origins(algo):
+    """Random rays from origins on cluster faces / integer coordinates (not on region-face corners, where the reference itself is
+    undefined): many of them crawl (the oracle executes > 10^8 cluster-skip iterations here), a few cross a binade boundary while
+    crawling -- the situations in which the first crawl_skip was off by one iteration.  Colours, hit voxels and event counters
+    must equal the C oracle's."""
+    po.set_lighting("orc")
+    xyz, rgb = scenes.sparse_shells(256, 32, seed=9, fill_pct=45)
+    s, ref = build_product(xyz, rgb, "vcs"), build_oracle("orc", xyz, rgb, "vcs")
+    s.set_statistics(True)
+    for i, origin in enumerate([(48.0, 240.0, 232.0), (208.0, 224.0, 16.0), (63.0, 39.0, 4.0)]):
+        rays = scenes.random_rays(60000 if i == 0 else 30000, origin, seed=205 - i)   # ray 51980 of the first set crosses x = 32 while crawling
+        got, want = s.trace_rays(rays, algo, want_hits=True), ref.trace_rays(rays, algo, want_counters=True)
+        st = s.get_statistics()
+        assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"]), origin
+        assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3]), origin
+    s.close()
