@@ -406,8 +406,10 @@ struct FlatRay
 		else
 		{
 			// One value carries both codes: cc = cluster id << 9 | in-cluster code.  A coordinate v in [0, 64) contributes
-			// (v & 7) | (v >> 3) << 9 = (v * 65) & 0xE07, shifted to its axis' place.
-			const uint32_t cc = ((((uint32_t)c0 * 65u) & 0xE07u) << sh[0]) | ((((uint32_t)c1 * 65u) & 0xE07u) << sh[1]) | ((((uint32_t)c2 * 65u) & 0xE07u) << sh[2]);
+			// (v & 7) | (v >> 3) << 9 = (v * 65) & 0x1E07, shifted to its axis' place.  (Bit 12 of the mask only matters for v = 64, the
+			// reference's undefined corner -- a ray rebased onto the far face of a region: it makes this form alias the coordinate
+			// into the neighbouring cluster id exactly like the nested form and the C oracle do.)
+			const uint32_t cc = ((((uint32_t)c0 * 65u) & 0x1E07u) << sh[0]) | ((((uint32_t)c1 * 65u) & 0x1E07u) << sh[1]) | ((((uint32_t)c2 * 65u) & 0x1E07u) << sh[2]);
 			// header word index inside the region = cid * 16 + code / 32 = cc >> 5; bit = code % 32 = cc % 32
 #if VRM_VCS_FUSED_EXIST
 			// ONE 8-byte load answers both questions: the word's .y carries the cluster-exists flag (vrm_build.cu)
