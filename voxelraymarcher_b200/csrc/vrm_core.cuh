@@ -281,6 +281,18 @@ template <class P, class T> VRM_HD void to_world(const P& p, const T* w, T* xyz)
 VRM_HD uint32_t hash_slot1(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 
+// A ray rebased onto the far face of a region can be looked up with a coordinate of exactly 64 (only from positions exactly on a
+// region face).  For y or z = 64 the reference's behaviour is defined: its cluster id aliases into a neighbouring cluster and its
+// key matches nothing, so the lookup is empty; ours can alias into voxel (.., 0, ..) of that cluster and find something.  These
+// switches make the lookup exact there ("a coordinate of 64 is never found").  OFF by default: measured cost 0.9 % on the state
+// machine, and the nested kernels lose 7-25 % (ptxas places their reconvergence points differently; hash + longest axis 3.10 ->
+// 3.92 ms) for a case the differential fuzz (tools/gpu_fuzz.py, ~10^7 rays from region-face origins) never saw change a pixel.
+#ifndef VRM_COORD64_EMPTY
+#define VRM_COORD64_EMPTY 0          // state machine (vrm_flat.cuh)
+#endif
+#ifndef VRM_COORD64_EMPTY_NESTED
+#define VRM_COORD64_EMPTY_NESTED 0   // nested form (lookup_voxel below)
+#endif
 #ifndef VRM_HASH_CLUSTER_FILTER
 #define VRM_HASH_CLUSTER_FILTER 1
 #endif
@@ -419,6 +431,12 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		uint32_t bit = code & 31;
 		if ((h.x >> bit) & 1u) v = ldg(c.sv.values + (h.y & ~kHeaderClusterExists) + popc32(h.x & ((1u << bit) - 1u)));
 	}
+#if VRM_COORD64_EMPTY_NESTED
+	// A ray rebased onto the far face of a region is looked up with a coordinate of exactly 64.  The reference's key for it
+	// (VoxelFunctions.cuh:41-46: x << 20 | y << 10 | z) matches no stored voxel, whatever cluster or slot the overflowing
+	// bits alias into -- so the answer is "empty" (only the cluster-exists test sees the aliased cluster).
+	if (((uint32_t)g0 | (uint32_t)g1 | (uint32_t)g2) & 64u) v = kEmpty;
+#endif
 	if (STATS) c.st.nLookup++;
 	if (v != kEmpty)
 	{

@@ -400,6 +400,9 @@ struct FlatRay
 				if ((uint32_t)(e1 >> 32) == key) col = (uint32_t)e1;
 				else if ((uint32_t)(e2 >> 32) == key) col = (uint32_t)e2;
 			}
+#if VRM_COORD64_EMPTY
+			if (((uint32_t)c0 | (uint32_t)c1 | (uint32_t)c2) & 64u) col = kEmpty;  // a coordinate of 64 matches no stored voxel (lookup_voxel, vrm_core.cuh)
+#endif
 			if (STATS) { c.st.nExist++; c.st.nLookup++; c.st.nProbe2++; if (col != kEmpty) c.st.nLookupHit++; }
 			return true;
 		}
@@ -425,7 +428,12 @@ struct FlatRay
 			const uint2 h = ldg(c.sv.headers + ((uint32_t)ri * 8192u + (cc >> 5)));
 #endif
 			const uint32_t bit = cc & 31u;
-			if ((h.x >> bit) & 1u) col = ldg(c.sv.values + ((h.y & ~kHeaderClusterExists) + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
+#if VRM_COORD64_EMPTY
+			const bool inRange = ((((uint32_t)c0 | (uint32_t)c1 | (uint32_t)c2) & 64u) == 0u);  // a coordinate of 64 matches no stored voxel (lookup_voxel, vrm_core.cuh)
+#else
+			const bool inRange = true;
+#endif
+			if (((h.x >> bit) & 1u) && inRange) col = ldg(c.sv.values + ((h.y & ~kHeaderClusterExists) + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
 			if (STATS) { c.st.nLookup++; if (col != kEmpty) c.st.nLookupHit++; }
 			return true;
 		}
