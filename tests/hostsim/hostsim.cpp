@@ -293,7 +293,7 @@ int sim_scene_build(void* h, int storageType)
 			{
 				uint32_t cid = v.first >> 9, code = v.first & 511;
 				uint32_t x = ((cid >> 6) << 3) | (code >> 6), y = (((cid >> 3) & 7) << 3) | ((code >> 3) & 7), z = ((cid & 7) << 3) | (code & 7);
-				unsigned long long e = ((unsigned long long)((x << 12) | (y << 6) | z) << 32) | v.second;
+				unsigned long long e = ((unsigned long long)hash_key(x, y, z) << 32) | v.second;
 				int table = 0, it = 0;
 				for (; it < 500; it++)
 				{

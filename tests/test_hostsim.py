@@ -231,6 +231,36 @@ def test_core_rays_starting_on_power_of_two_coordinates(algo):
         assert np.array_equal(ta[k], tb[k]), k
 
 
+def coordinate64_rays():
+    """Rays from (128, 64, 0) * 1/8 of the probe scene (scale 8): a corner shared by eight regions.  Their first EPSILON step leaves the
+    region at -tiny on the two short axes and is rebased to exactly 64.0f, so the longest-axis walk tests voxels with a coordinate of 64
+    before its grid values are back inside the region (found by tools/stress_diff.py, seed 77)."""
+    bits = [(0xbbd13b05, 0xbba7a053, 0xbf7ffdce), (0xbc37ff18, 0xbc19b7c9, 0xbf7ff8fb), (0xbc76f148, 0xbb6a7051, 0xbf7ff823),
+            (0xbf7ff978, 0xbbf7f442, 0xbc435e2e), (0xbc6cd52e, 0xbacde9b9, 0xbf7ff912), (0xbf7ff3e6, 0xbc26e79f, 0xbc8582e4)]
+    rays = np.zeros((len(bits), 6), np.float32)
+    rays[:, :3] = (16.0, 8.0, -0.0)
+    rays[:, 3:] = np.array(bits, np.uint32).view(np.float32)
+    return rays
+
+
+@pytest.mark.parametrize("storage", ["vcs", "hashtable"])
+def test_core_lookups_with_a_coordinate_of_64_are_empty(storage, traversal_form):
+    """A lookup with a region-local coordinate of exactly 64 matches no stored voxel in the reference (its key x << 20 | y << 10 | z
+    differs from every stored key), whatever cluster the overflowing bits alias into.  Six-bit packed codes would alias into voxel
+    (.., 0, ..) of the neighbouring cluster row and these rays would hit voxel (127, 64, -1), which the reference passes."""
+    if storage == "vcs" and traversal_form == "nested":
+        pytest.skip("VCS + longest axis runs on the state machine; the nested form has the test behind VRM_COORD64_EMPTY_NESTED (vrm_core.cuh)")
+    po.set_lighting("orc")
+    po.set_lighting("sim")
+    xyz, rgb = scenes.probe_scene()
+    a, b = build_oracle("orc", xyz, rgb, storage), build_oracle("sim", xyz, rgb, storage)
+    rays = coordinate64_rays()
+    ta, tb = a.trace_rays(rays, "longestaxis", scale=8), b.trace_rays(rays, "longestaxis", scale=8)
+    assert not ta["hits"][:, 3].any()
+    for k in ("colour", "hits"):
+        assert np.array_equal(ta[k], tb[k]), k
+
+
 def test_crawl_skip_equals_the_iterations_it_replaces():
     """Brute force: 60 000 pseudo-random crawl situations (positions on cluster faces / integers / powers of two and a few ulps around
     them; EPSILON steps from "cannot move" to hundreds of ulps).  Whenever crawl_skip fast-forwards, executing the skipped iterations

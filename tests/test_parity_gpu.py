@@ -507,6 +507,22 @@ def test_rays_starting_on_power_of_two_coordinates(algo):
     s.close()
 
 
+@pytest.mark.parametrize("storage", ["vcs", "hashtable"])
+def test_lookups_with_a_coordinate_of_64_are_empty(storage):
+    """tests/test_hostsim.py coordinate64_rays through the kernels: rays rebased onto exactly 64.0 test voxels with a coordinate of 64,
+    which match nothing in the reference.  (These exact rays cannot be had from a camera: the render kernels' source is covered by
+    its host compile in tests/test_hostsim.py for this case.)"""
+    from tests.test_hostsim import coordinate64_rays
+    po.set_lighting("orc")
+    xyz, rgb = scenes.probe_scene()
+    s, ref = build_product(xyz, rgb, storage), build_oracle("orc", xyz, rgb, storage)
+    rays = coordinate64_rays()
+    got, want = s.trace_rays(rays, "longestaxis", scale=8, want_hits=True), ref.trace_rays(rays, "longestaxis", scale=8)
+    assert not want["hits"][:, 3].any()
+    assert np.array_equal(got["colour"], want["colour"]) and np.array_equal(got["hits"], want["hits"])
+    s.close()
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("algo", ["original", "longestaxis"])
 def test_trace_fuzz_from_grid_aligned_origins(algo):

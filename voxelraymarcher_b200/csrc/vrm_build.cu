@@ -348,7 +348,7 @@ __global__ void cuckoo_insert_kernel(const unsigned long long* __restrict__ ukey
 	unsigned long long k = ukeys[j];
 	uint32_t cid = (uint32_t)(k >> 9) & 511u, code = (uint32_t)k & 511u;
 	uint32_t x = ((cid >> 6) << 3) | (code >> 6), y = (((cid >> 3) & 7u) << 3) | ((code >> 3) & 7u), z = ((cid & 7u) << 3) | (code & 7u);
-	unsigned long long entry = ((unsigned long long)((x << 12) | (y << 6) | z) << 32) | uvals[j];
+	unsigned long long entry = ((unsigned long long)vrm::hash_key(x, y, z) << 32) | uvals[j];
 	unsigned long long* t1 = slots + d.slotBase;
 	unsigned long long* t2 = t1 + d.n;
 	int table = 0;

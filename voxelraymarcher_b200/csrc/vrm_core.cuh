@@ -206,7 +206,7 @@ struct SceneView
 	int32_t minCoord;
 	// cuckoo hash table ("two-level": region directory -> per-region pair of tables)
 	const HashRegionDesc* hashDesc;
-	const unsigned long long* slots;  // (key18 << 32) | rgb ; kEmptySlot when free
+	const unsigned long long* slots;  // (hash_key << 32) | rgb ; kEmptySlot when free
 	// voxel cluster store
 	const uint2* headers;         // [region][512 clusters][16 words] {occupancy mask, index of the word's first colour}
 	const uint32_t* clusterMask;  // [region][16] : bit c set <=> cluster c holds at least one voxel
@@ -222,11 +222,12 @@ struct Stats
 // ---------------------------------------------------------------- axis permutation ("walk space")
 
 // Walk slot i holds world axis axis(i).  cs(i) = shift of that axis inside a 9-bit cluster / in-cluster code
-// (x:6, y:3, z:0 -- VoxelClusterStore.cuh:21-24); the 18-bit hash key uses shift 2*cs(i) (x:12, y:6, z:0).
+// (x:6, y:3, z:0 -- VoxelClusterStore.cuh:21-24); ks(i) = its shift inside the hash key (x:14, y:7, z:0 -- hash_key below).
 struct PermIdentity
 {
 	VRM_HD int axis(int i) const { return i; }
 	VRM_HD int cs(int i) const { return 6 - 3 * i; }
+	VRM_HD int ks(int i) const { return 14 - 7 * i; }
 	VRM_HD uint32_t stride(int i, uint32_t D) const { return i == 0 ? 1u : (i == 1 ? D : D * D); }
 };
 
@@ -235,6 +236,7 @@ struct PermRuntime
 	int a0, a1, a2;
 	VRM_HD int axis(int i) const { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 	VRM_HD int cs(int i) const { return 6 - 3 * axis(i); }
+	VRM_HD int ks(int i) const { return 14 - 7 * axis(i); }
 	VRM_HD uint32_t stride(int i, uint32_t D) const
 	{
 		int a = axis(i);
@@ -281,14 +283,18 @@ template <class P, class T> VRM_HD void to_world(const P& p, const T* w, T* xyz)
 VRM_HD uint32_t hash_slot1(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mulhi32((key + 1u) * seed, n); }
 
-// A ray rebased onto the far face of a region can be looked up with a coordinate of exactly 64 (only from positions exactly on a
-// region face).  For y or z = 64 the reference's behaviour is defined: its cluster id aliases into a neighbouring cluster and its
-// key matches nothing, so the lookup is empty; ours can alias into voxel (.., 0, ..) of that cluster and find something.  These
-// switches make the lookup exact there ("a coordinate of 64 is never found").  OFF by default: measured cost 0.9 % on the state
-// machine, and the nested kernels lose 7-25 % (ptxas places their reconvergence points differently; hash + longest axis 3.10 ->
-// 3.92 ms) for a case the differential fuzz (tools/gpu_fuzz.py, ~10^7 rays from region-face origins) never saw change a pixel.
+// "A coordinate of 64".  A ray that leaves a region through a low face at -tiny is rebased to 64 - tiny, which rounds to exactly
+// 64.0f for tiny < 2^-19: the longest-axis walk then tests up to two voxels with a coordinate of 64 before its grid values are
+// back inside the region (the original algorithm never does: it tests isRayInRegion first).  In the reference such a lookup is
+// always empty for y or z = 64 -- its cluster id aliases into a neighbouring cluster, which only doesVoxelSpaceExist sees, and its
+// key matches nothing (x = 64 indexes past its 512-entry cluster table: undefined there).  Here:
+//  * hash table: the key has a spare bit per coordinate (hash_key below), so 64 matches nothing -- no extra instruction;
+//  * VCS, state machine (the form every longest-axis default uses): tested behind the occupancy bit (vrm_flat.cuh voxel_test),
+//    VRM_COORD64_EMPTY (default 1);
+//  * VCS, nested form (reachable only with VRM_RENDER_MODE=1 for the longest axis): VRM_COORD64_EMPTY_NESTED, default 0 -- the
+//    nested kernels depend on where ptxas places their reconvergence points and lose 7-25 % to the extra test.
 #ifndef VRM_COORD64_EMPTY
-#define VRM_COORD64_EMPTY 0          // state machine (vrm_flat.cuh)
+#define VRM_COORD64_EMPTY 1          // state machine (vrm_flat.cuh)
 #endif
 #ifndef VRM_COORD64_EMPTY_NESTED
 #define VRM_COORD64_EMPTY_NESTED 0   // nested form (lookup_voxel below)
@@ -297,11 +303,18 @@ VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mul
 #define VRM_HASH_CLUSTER_FILTER 1
 #endif
 template <class T> VRM_HD T ldg(const T* p);
-// key = x << 12 | y << 6 | z (region-local, 6 bits each) -> cluster id (x/8) << 6 | (y/8) << 3 | z/8 -> bit of the region's mask
+// The hash key of a region-local voxel: x << 14 | y << 7 | z -- SEVEN bits per coordinate although a stored voxel needs six.  The
+// traversal can ask for a coordinate of exactly 64 (a ray rebased onto the far face of a region); the reference's key for it
+// (VoxelFunctions.cuh:41-46: x << 20 | y << 10 | z) matches no stored voxel, and with the spare bit neither does this one --
+// a 6-bit field would carry into its neighbour and could match a voxel of the next row.  Costs nothing: same instructions.
+constexpr int kHashKeyBits = 7;
+VRM_HD uint32_t hash_key(uint32_t x, uint32_t y, uint32_t z) { return (x << (2 * kHashKeyBits)) | (y << kHashKeyBits) | z; }
+// key -> cluster id (x/8) << 6 | (y/8) << 3 | z/8 -> bit of the region's mask (a coordinate of 64 lands in row 0 of its axis:
+// whatever the filter answers there, the key comparison still fails)
 VRM_HD bool hash_cluster_occupied(const uint32_t* clusterMask, uint32_t ri, uint32_t key)
 {
 	const uint32_t t = key >> 3;
-	const uint32_t cid = (t & 7u) | ((t >> 3) & 0x38u) | ((t >> 6) & 0x1C0u);
+	const uint32_t cid = (t & 7u) | ((t >> 4) & 0x38u) | ((t >> 8) & 0x1C0u);
 	return ((ldg(clusterMask + (ri * 16u + (cid >> 5))) >> (cid & 31u)) & 1u) != 0u;
 }
 
@@ -406,7 +419,7 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 	if constexpr (ST == kStorageHash)
 	{
 		const RegionRef<kStorageHash>& rh = r;
-		uint32_t key = ((uint32_t)g0 << (2 * p.cs(0))) | ((uint32_t)g1 << (2 * p.cs(1))) | ((uint32_t)g2 << (2 * p.cs(2)));
+		uint32_t key = ((uint32_t)g0 << p.ks(0)) | ((uint32_t)g1 << p.ks(1)) | ((uint32_t)g2 << p.ks(2));
 #if VRM_HASH_CLUSTER_FILTER
 		// negative filter: a voxel whose 8^3 cluster holds no voxel at all cannot be in the table, and the 64-byte mask of the
 		// region answers that from L1 -- most lookups of a walk through open space never touch the (much larger) slot arrays.
@@ -435,7 +448,7 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 	// A ray rebased onto the far face of a region is looked up with a coordinate of exactly 64.  The reference's key for it
 	// (VoxelFunctions.cuh:41-46: x << 20 | y << 10 | z) matches no stored voxel, whatever cluster or slot the overflowing
 	// bits alias into -- so the answer is "empty" (only the cluster-exists test sees the aliased cluster).
-	if (((uint32_t)g0 | (uint32_t)g1 | (uint32_t)g2) & 64u) v = kEmpty;
+	if constexpr (ST == kStorageVcs) { if (((uint32_t)g0 | (uint32_t)g1 | (uint32_t)g2) & 64u) v = kEmpty; }  // (the hash key already matches nothing)
 #endif
 	if (STATS) c.st.nLookup++;
 	if (v != kEmpty)

@@ -166,7 +166,7 @@ struct FlatRay
 	uint32_t ur[3];       // region coordinates minus minCoord (walk space); in the table <=> all < diameter
 	int32_t ri;           // table entry of the region under the ray: dense region index, -1 null region, -2 outside the table
 	RegionRef<ST> r;      // hash table: the region's descriptor (the VCS addresses everything from ri)
-	uint32_t sh[3];       // walk slot -> shift of its coordinate inside a storage code (VCS: 6/3/0 per world x/y/z; hash key: 12/6/0)
+	uint32_t sh[3];       // walk slot -> shift of its coordinate inside a storage code (VCS: 6/3/0 per world x/y/z; hash key: 14/7/0)
 	uint32_t rs[3];       // walk slot -> stride of its coordinate in the region table (1, D, D*D per world x/y/z)
 	int st;
 	int mode;             // AdvMode of the next kStMain step; a pending hit (kStHit) keeps its packed normal / shadow-routine bits here
@@ -195,7 +195,7 @@ struct FlatRay
 		const int a[3] = {p.a0, p.a1, p.a2};
 		for (int i = 0; i < 3; i++)
 		{
-			sh[i] = (uint32_t)(6 - 3 * a[i]) * (ST == kStorageHash ? 2u : 1u);
+			sh[i] = ST == kStorageHash ? (uint32_t)(kHashKeyBits * (2 - a[i])) : (uint32_t)(6 - 3 * a[i]);
 			rs[i] = a[i] == 0 ? 1u : (a[i] == 1 ? D : D * D);
 		}
 	}
@@ -400,9 +400,6 @@ struct FlatRay
 				if ((uint32_t)(e1 >> 32) == key) col = (uint32_t)e1;
 				else if ((uint32_t)(e2 >> 32) == key) col = (uint32_t)e2;
 			}
-#if VRM_COORD64_EMPTY
-			if (((uint32_t)c0 | (uint32_t)c1 | (uint32_t)c2) & 64u) col = kEmpty;  // a coordinate of 64 matches no stored voxel (lookup_voxel, vrm_core.cuh)
-#endif
 			if (STATS) { c.st.nExist++; c.st.nLookup++; c.st.nProbe2++; if (col != kEmpty) c.st.nLookupHit++; }
 			return true;
 		}
@@ -428,12 +425,17 @@ struct FlatRay
 			const uint2 h = ldg(c.sv.headers + ((uint32_t)ri * 8192u + (cc >> 5)));
 #endif
 			const uint32_t bit = cc & 31u;
+			if ((h.x >> bit) & 1u)
+			{
+				col = ldg(c.sv.values + ((h.y & ~kHeaderClusterExists) + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
 #if VRM_COORD64_EMPTY
-			const bool inRange = ((((uint32_t)c0 | (uint32_t)c1 | (uint32_t)c2) & 64u) == 0u);  // a coordinate of 64 matches no stored voxel (lookup_voxel, vrm_core.cuh)
-#else
-			const bool inRange = true;
+				// Only the longest-axis walk can ask for a coordinate of exactly 64 (the first tests after entering a region on its far
+				// face, see vrm_core.cuh "a coordinate of 64"); the reference's key for it matches no stored voxel.  Applied HERE, after
+				// the (in-bounds: the aliased cluster is a real one) load behind the occupancy bit, so that only a lookup that found
+				// something pays for it -- the walk through empty space does not.
+				if constexpr (kLA) { if (((uint32_t)c0 | (uint32_t)c1 | (uint32_t)c2) & 64u) col = kEmpty; }
 #endif
-			if (((h.x >> bit) & 1u) && inRange) col = ldg(c.sv.values + ((h.y & ~kHeaderClusterExists) + (uint32_t)popc32(h.x & ((1u << bit) - 1u))));
+			}
 			if (STATS) { c.st.nLookup++; if (col != kEmpty) c.st.nLookupHit++; }
 			return true;
 		}
