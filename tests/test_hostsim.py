@@ -261,6 +261,24 @@ def test_core_lookups_with_a_coordinate_of_64_are_empty(storage, traversal_form)
         assert np.array_equal(ta[k], tb[k]), k
 
 
+@pytest.mark.parametrize("storage,algo", [("hashtable", "longestaxis"), ("hashtable", "original"), ("vcs", "original")])
+def test_core_render_from_region_corner_cameras(storage, algo):
+    """Cameras exactly on a corner shared by eight regions, looking along the faces (tests/test_parity_gpu.py has the same case on the
+    kernels): everything the hash table and the original algorithm do there is defined in the reference, so rgb, hit voxels and every
+    event counter must match."""
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    po.set_lighting("sim")
+    xyz, rgb = scenes.probe_scene()
+    a, b = build_oracle(kind, xyz, rgb, storage), build_oracle("sim", xyz, rgb, storage)
+    for o, l in (((16.0, 8.0, 0.0), (15.9, 7.9, -10.0)), ((8.0, 16.0, 8.0), (7.95, 0.0, 7.9))):
+        cam = camera(o, l, 60.0, 192, 108, kind)
+        ra = a.render(cam, 192, 108, algo, scale=8, want_counters=True, want_lookups=True)
+        rb = b.render(cam, 192, 108, algo, scale=8, want_counters=True, want_lookups=True)
+        for k in ("rgb", "hits", "counters", "lookups"):
+            assert np.array_equal(ra[k], rb[k]), (storage, algo, o, k)
+
+
 def test_crawl_skip_equals_the_iterations_it_replaces():
     """Brute force: 60 000 pseudo-random crawl situations (positions on cluster faces / integers / powers of two and a few ulps around
     them; EPSILON steps from "cannot move" to hundreds of ulps).  Whenever crawl_skip fast-forwards, executing the skipped iterations

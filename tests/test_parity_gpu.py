@@ -523,6 +523,31 @@ def test_lookups_with_a_coordinate_of_64_are_empty(storage):
     s.close()
 
 
+REGION_CORNER_CAMERAS = [((16.0, 8.0, 0.0), (15.9, 7.9, -10.0)), ((8.0, 16.0, 8.0), (7.95, 0.0, 7.9)), ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0))]
+
+
+@pytest.mark.parametrize("storage,algo", [("hashtable", "longestaxis"), ("hashtable", "original"), ("vcs", "original")])
+def test_render_from_region_corner_cameras(probe, storage, algo):
+    """Cameras sitting exactly on a corner shared by eight regions (scale 8: (128, 64, 0), (64, 128, 64), (64, 64, 64)) looking
+    along the faces: the frames where rays are rebased onto exactly 64.0.  The hash table is defined everywhere there (no cluster
+    table to overrun, a key with a coordinate of 64 matches nothing) and so is the original algorithm; VCS + longest axis is left
+    out because the reference's exists test is undefined at x = 64."""
+    xyz, rgb = probe
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    ref, s = build_oracle(kind, xyz, rgb, storage), build_product(xyz, rgb, storage)
+    s.set_statistics(True)
+    for o, l in REGION_CORNER_CAMERAS:
+        cam = api.Camera(o, l, (0.0, 1.0, 0.0), 60.0, np.float32(320) / np.float32(180))
+        got = s.render(320, 180, algo, cam, scale=8, want_hits=True)
+        st = s.get_statistics()
+        want = ref.render(cam.data, 320, 180, algo, scale=8, want_counters=True)
+        assert np.array_equal(got["hits"], want["hits"]), (storage, algo, o, int((got["hits"] != want["hits"]).any(-1).sum()))
+        assert np.array_equal(got["rgb"], want["rgb"]), (storage, algo, o)
+        assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3]), (storage, algo, o)
+    s.close()
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("algo", ["original", "longestaxis"])
 def test_trace_fuzz_from_grid_aligned_origins(algo):
