@@ -244,12 +244,10 @@ def coordinate64_rays():
 
 
 @pytest.mark.parametrize("storage", ["vcs", "hashtable"])
-def test_core_lookups_with_a_coordinate_of_64_are_empty(storage, traversal_form):
+def test_core_lookups_with_a_coordinate_of_64_are_empty(storage):
     """A lookup with a region-local coordinate of exactly 64 matches no stored voxel in the reference (its key x << 20 | y << 10 | z
     differs from every stored key), whatever cluster the overflowing bits alias into.  Six-bit packed codes would alias into voxel
     (.., 0, ..) of the neighbouring cluster row and these rays would hit voxel (127, 64, -1), which the reference passes."""
-    if storage == "vcs" and traversal_form == "nested":
-        pytest.skip("VCS + longest axis runs on the state machine; the nested form has the test behind VRM_COORD64_EMPTY_NESTED (vrm_core.cuh)")
     po.set_lighting("orc")
     po.set_lighting("sim")
     xyz, rgb = scenes.probe_scene()

@@ -243,6 +243,8 @@ struct PermRuntime
 		return a == 0 ? 1u : (a == 1 ? D : D * D);
 	}
 };
+template <class P> constexpr bool kIsIdentityPerm = false;
+template <> constexpr bool kIsIdentityPerm<PermIdentity> = true;
 
 // Ray::convertRayToLongestAxisDirection, renderer/rays/Ray.cuh:19-71 (strict '>' tie rules): slot 0 = longest,
 // slot 1 = "shortAxis1" (middle), slot 2 = "shortAxis2" (shortest).
@@ -289,15 +291,11 @@ VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mul
 // always empty for y or z = 64 -- its cluster id aliases into a neighbouring cluster, which only doesVoxelSpaceExist sees, and its
 // key matches nothing (x = 64 indexes past its 512-entry cluster table: undefined there).  Here:
 //  * hash table: the key has a spare bit per coordinate (hash_key below), so 64 matches nothing -- no extra instruction;
-//  * VCS, state machine (the form every longest-axis default uses): tested behind the occupancy bit (vrm_flat.cuh voxel_test),
-//    VRM_COORD64_EMPTY (default 1);
-//  * VCS, nested form (reachable only with VRM_RENDER_MODE=1 for the longest axis): VRM_COORD64_EMPTY_NESTED, default 0 -- the
-//    nested kernels depend on where ptxas places their reconvergence points and lose 7-25 % to the extra test.
+//  * VCS: the longest-axis test sites (vrm_flat.cuh voxel_test, lookup_voxel below with a run-time permutation) reject the
+//    coordinate AFTER the value load behind the occupancy bit -- only a lookup that found something executes it, the walk through
+//    empty space pays nothing (measured: 1.504 ms before and after).  VRM_COORD64_EMPTY=0 removes it.
 #ifndef VRM_COORD64_EMPTY
-#define VRM_COORD64_EMPTY 1          // state machine (vrm_flat.cuh)
-#endif
-#ifndef VRM_COORD64_EMPTY_NESTED
-#define VRM_COORD64_EMPTY_NESTED 0   // nested form (lookup_voxel below)
+#define VRM_COORD64_EMPTY 1
 #endif
 #ifndef VRM_HASH_CLUSTER_FILTER
 #define VRM_HASH_CLUSTER_FILTER 1
@@ -442,14 +440,14 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		uint32_t code = ((uint32_t)(g0 & 7) << p.cs(0)) | ((uint32_t)(g1 & 7) << p.cs(1)) | ((uint32_t)(g2 & 7) << p.cs(2));
 		uint2 h = ldg(c.sv.headers + (((size_t)rv.ri * 512 + cid) * 16 + (code >> 5)));
 		uint32_t bit = code & 31;
-		if ((h.x >> bit) & 1u) v = ldg(c.sv.values + (h.y & ~kHeaderClusterExists) + popc32(h.x & ((1u << bit) - 1u)));
+		if ((h.x >> bit) & 1u)
+		{
+			v = ldg(c.sv.values + (h.y & ~kHeaderClusterExists) + popc32(h.x & ((1u << bit) - 1u)));
+			// "a coordinate of 64" (above): only the longest-axis walk (the one with a run-time permutation) can ask for it; applied
+			// after the load behind the occupancy bit, like the state machine's test site (vrm_flat.cuh voxel_test)
+			if constexpr (VRM_COORD64_EMPTY && !kIsIdentityPerm<P>) { if (((uint32_t)g0 | (uint32_t)g1 | (uint32_t)g2) & 64u) v = kEmpty; }
+		}
 	}
-#if VRM_COORD64_EMPTY_NESTED
-	// A ray rebased onto the far face of a region is looked up with a coordinate of exactly 64.  The reference's key for it
-	// (VoxelFunctions.cuh:41-46: x << 20 | y << 10 | z) matches no stored voxel, whatever cluster or slot the overflowing
-	// bits alias into -- so the answer is "empty" (only the cluster-exists test sees the aliased cluster).
-	if constexpr (ST == kStorageVcs) { if (((uint32_t)g0 | (uint32_t)g1 | (uint32_t)g2) & 64u) v = kEmpty; }  // (the hash key already matches nothing)
-#endif
 	if (STATS) c.st.nLookup++;
 	if (v != kEmpty)
 	{
