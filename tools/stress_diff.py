@@ -7,7 +7,9 @@ crawl_skip defects of round 1; run it after touching any fast-forward.
 
 Oracle = oracle/vrm_oracle.c ("orc"): it has defined behaviour where the reference's host build reads past its 512-entry cluster
 table (a ray rebased onto local coordinate 64.0 -- origins with a coordinate on a region face provoke it; such mismatches are reported as
-"origin on a region face" and are not counted as defects: nothing defined exists to match there)."""
+"origin on a region face" and are not counted as defects: nothing defined exists to match there -- the oracle's own event counters
+vary from run to run for such rays, its cluster table being followed by the next region's struct.  Lookups with y or z = 64 ARE defined
+(empty) and exact since round 1; colour / hit differences from such origins are therefore listed separately at the end)."""
 import os, sys
 import numpy as np
 
@@ -24,6 +26,7 @@ def main():
     rng = np.random.default_rng(seed)
     cases = [("shells512", scenes.sparse_shells(512, 64, seed=21, fill_pct=30), 1), ("terrain192", scenes.terrain(192, 9), 1), ("probe", scenes.probe_scene(), 8)]
     defects = 0
+    corner_pixels = 0
     for name, (xyz, rgb), scale in cases:
         lo, hi = xyz.min(0), xyz.max(0)
         origins = []
@@ -51,10 +54,11 @@ def main():
                         print(f"MISMATCH{' (origin on a region face: the reference can be undefined)' if corner else ''} {name} {storage} {algo} origin {org} {'state machine' if flat else 'nested'}: "
                               f"oracle {ta['counters'][:3]} product {tb['counters'][:3]}, {bad} rays differ in colour / hit", flush=True)
                         defects += 0 if corner else 1
+                        corner_pixels += bad if corner else 0
             print(name, storage, algo, "done", flush=True)
             a.close(); b.close()
     lib.sim_set_flat(1)
-    print("defects:", defects)
+    print("defects:", defects, " rays differing in colour / hit from region-face origins (undefined corner):", corner_pixels)
     return 1 if defects else 0
 
 
