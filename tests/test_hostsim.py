@@ -253,9 +253,10 @@ def test_core_lookups_with_a_coordinate_of_64_are_empty(storage):
     xyz, rgb = scenes.probe_scene()
     a, b = build_oracle("orc", xyz, rgb, storage), build_oracle("sim", xyz, rgb, storage)
     rays = coordinate64_rays()
-    ta, tb = a.trace_rays(rays, "longestaxis", scale=8), b.trace_rays(rays, "longestaxis", scale=8)
+    ta, tb = a.trace_rays(rays, "longestaxis", scale=8, want_counters=True), b.trace_rays(rays, "longestaxis", scale=8, want_counters=True)
     assert not ta["hits"][:, 3].any()
-    for k in ("colour", "hits"):
+    # (event counters only for the hash table: the VCS exists test of the reference is undefined when the coordinate of 64 is x)
+    for k in ("colour", "hits") + (("counters",) if storage == "hashtable" else ()):
         assert np.array_equal(ta[k], tb[k]), k
 
 
