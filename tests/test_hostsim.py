@@ -231,6 +231,25 @@ def test_core_rays_starting_on_power_of_two_coordinates(algo):
         assert np.array_equal(ta[k], tb[k]), k
 
 
+@pytest.mark.parametrize("storage,algo", COMBOS)
+def test_core_scene_translation(storage, algo):
+    """VoxelSceneInfo's translation vector (Main.cu:215 always passes zero, the routines take any): ray origins are moved by
+    -translation before scaling and the lighting positions by +translation (Renderer.cuh:338-341, 821-822)."""
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    po.set_lighting("sim")
+    xyz, rgb = scenes.probe_scene()
+    a, b = build_oracle(kind, xyz, rgb, storage), build_oracle("sim", xyz, rgb, storage)
+    o, l, fov = PROBE_CAMERAS[1]
+    cam = camera(o, l, fov, 160, 90, kind)
+    for tr in ((3.5, -2.25, 7.0), (-0.3, 0.7, 0.1)):
+        ra = a.render(cam, 160, 90, algo, scale=8, translation=tr, want_counters=True, want_lookups=True)
+        rb = b.render(cam, 160, 90, algo, scale=8, translation=tr, want_counters=True, want_lookups=True)
+        assert (ra["hits"][..., 3] != 0).sum() > 1000
+        for k in ("rgb", "hits", "counters", "lookups"):
+            assert np.array_equal(ra[k], rb[k]), (storage, algo, tr, k)
+
+
 def coordinate64_rays():
     """Rays from (128, 64, 0) * 1/8 of the probe scene (scale 8): a corner shared by eight regions.  Their first EPSILON step leaves the
     region at -tiny on the two short axes and is rebased to exactly 64.0f, so the longest-axis walk tests voxels with a coordinate of 64

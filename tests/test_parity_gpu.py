@@ -523,6 +523,27 @@ def test_lookups_with_a_coordinate_of_64_are_empty(storage):
     s.close()
 
 
+@pytest.mark.parametrize("storage,algo", COMBOS)
+def test_scene_translation_matches_oracle(probe, storage, algo):
+    """A non-zero VoxelSceneInfo translation (the reference's main always passes zero; its routines and this ABI take any) through
+    the render and the trace kernels."""
+    xyz, rgb = probe
+    kind = oracle_kind()
+    po.set_lighting(kind)
+    ref, s = build_oracle(kind, xyz, rgb, storage), build_product(xyz, rgb, storage)
+    o, l, fov = PROBE_CAMERAS[1]
+    cam = api.Camera(o, l, (0.0, 1.0, 0.0), fov, np.float32(320) / np.float32(180))
+    for tr in ((3.5, -2.25, 7.0), (-0.3, 0.7, 0.1)):
+        got = s.render(320, 180, algo, cam, scale=8, translation=tr, want_hits=True)
+        want = ref.render(cam.data, 320, 180, algo, scale=8, translation=tr)
+        assert (want["hits"][..., 3] != 0).sum() > 4000
+        assert np.array_equal(got["hits"], want["hits"]) and np.array_equal(got["rgb"], want["rgb"]), (storage, algo, tr)
+        rays = scenes.random_rays(20000, (o[0] + 0.25, o[1], o[2]), seed=77)
+        gt, wt = s.trace_rays(rays, algo, scale=8, translation=tr, want_hits=True), ref.trace_rays(rays, algo, scale=8, translation=tr)
+        assert np.array_equal(gt["colour"], wt["colour"]) and np.array_equal(gt["hits"], wt["hits"]), (storage, algo, tr)
+    s.close()
+
+
 REGION_CORNER_CAMERAS = [((16.0, 8.0, 0.0), (15.9, 7.9, -10.0)), ((8.0, 16.0, 8.0), (7.95, 0.0, 7.9)), ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0))]
 
 
