@@ -544,6 +544,49 @@ def test_scene_translation_matches_oracle(probe, storage, algo):
     s.close()
 
 
+@pytest.mark.parametrize("storage", ["vcs", "hashtable"])
+def test_device_pointer_entry_points_on_a_caller_stream(probe, storage):
+    """vrm_scene_add_voxels_device / vrm_render_device / vrm_trace_rays_device on the caller's stream (the path a framework with its
+    own device buffers takes, and the one bench.py times): same structure and same bytes as the host-buffer entry points; the opt-in
+    L2 access-policy window changes nothing but cache behaviour."""
+    import torch
+    xyz, rgb = probe
+    host = build_product(xyz, rgb, storage)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        d_xyz = torch.from_numpy(np.ascontiguousarray(xyz, np.int32)).cuda()
+        d_rgb = torch.from_numpy(np.ascontiguousarray(rgb, np.uint32).view(np.int32)).cuda()
+        s = api.VoxelScene(0)
+        s.set_stream(stream.cuda_stream)
+        half = len(rgb) // 2      # two chunks: staging keeps the insertion order across calls
+        s.add_voxels_device(d_xyz.data_ptr(), d_rgb.data_ptr(), half)
+        s.add_voxels_device(d_xyz[half:].data_ptr(), d_rgb[half:].data_ptr(), len(rgb) - half)
+        s.generate_voxel_scene(storage)
+        assert s.info() == host.info()
+        o, l, fov = PROBE_CAMERAS[1]
+        cam = api.Camera(o, l, (0.0, 1.0, 0.0), fov, np.float32(320) / np.float32(180))
+        rays = scenes.random_rays(20000, o, seed=3)
+        d_rays = torch.from_numpy(rays).cuda()
+        for algo in ("longestaxis", "original"):
+            want = host.render(320, 180, algo, cam, scale=8, want_hits=True)
+            wt = host.trace_rays(rays, algo, scale=8, want_hits=True)
+            for l2 in (False, True):
+                s.set_l2_persistence(l2)
+                fb = torch.zeros(180, 320, 3, dtype=torch.uint8, device="cuda")
+                hits = torch.zeros(180, 320, 4, dtype=torch.int32, device="cuda")
+                s.render_device(320, 180, algo, cam, fb.data_ptr(), hits.data_ptr(), scale=8)
+                colour = torch.zeros(len(rays), dtype=torch.int32, device="cuda")
+                rh = torch.zeros(len(rays), 4, dtype=torch.int32, device="cuda")
+                s.trace_rays_device(d_rays.data_ptr(), len(rays), algo, colour.data_ptr(), rh.data_ptr(), scale=8)
+                stream.synchronize()   # the calls are asynchronous on the caller's stream
+                assert np.array_equal(fb.cpu().numpy(), want["rgb"]) and np.array_equal(hits.cpu().numpy(), want["hits"]), (storage, algo, l2)
+                assert np.array_equal(colour.cpu().numpy().view(np.uint32), wt["colour"]) and np.array_equal(rh.cpu().numpy(), wt["hits"]), (storage, algo, l2)
+        s.reset_stream()
+        got = s.render(320, 180, "longestaxis", cam, scale=8)
+        assert np.array_equal(got["rgb"], host.render(320, 180, "longestaxis", cam, scale=8)["rgb"])
+    s.close(); host.close()
+
+
 REGION_CORNER_CAMERAS = [((16.0, 8.0, 0.0), (15.9, 7.9, -10.0)), ((8.0, 16.0, 8.0), (7.95, 0.0, 7.9)), ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0))]
 
 
