@@ -105,3 +105,53 @@ def test_sharded_blocks_equal_single_launch():
         parts.append(out)
     assert torch.equal(torch.cat(parts, 0), whole)
     assert whole.any()
+
+
+def _peer_worker(rank, world, port, q):
+    """Two processes on ONE GPU: rank 1 maps rank 0's frame buffer through CUDA IPC and its render kernel stores into it."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        xyz, rgb = scenes.probe_scene()
+        w, h, n = 320, 180, 5
+        cams = [api.Camera((6.0 + 0.7 * i, 2.0 + 0.3 * i, 6.0 - 0.5 * i), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h)) for i in range(n)]
+        s = api.VoxelScene(0)
+        s.add_voxels(xyz, rgb)
+        s.generate_voxel_scene("vcs")          # the structure is replicated: every rank builds its own
+        buf = multigpu.PeerFrameBuffer(n, w, h, 0)
+        mine = multigpu.shard_views_interleaved(n, world, rank)
+        if mine:
+            # round-robin shard in ONE launch: view v of this rank goes to global slot rank + v * world
+            s.render_views_device(w, h, "longestaxis", [cams[i] for i in mine], buf.ptr_for(rank), view_stride=world)
+        s.synchronize()
+        dist.barrier()                          # (bench.py uses a 4-byte all-reduce for the same purpose)
+        if rank == 0:
+            gathered = buf.to_tensor().cpu().numpy()
+            local = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda:0")
+            s.render_views_device(w, h, "longestaxis", cams, local.data_ptr())
+            s.synchronize()
+            q.put((bool(np.array_equal(gathered, local.cpu().numpy())), int(gathered.any(axis=(1, 2, 3)).sum())))
+        dist.barrier()                          # the owner frees the buffer only after every rank is done with it
+        buf.close()
+        s.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_fused_peer_memory_exchange_two_processes_one_gpu():
+    """vrm_peer_alloc / vrm_peer_open / vrm_copy_device / vrm_peer_close / vrm_peer_free with real CUDA IPC between two processes
+    (both on GPU 0, so it runs on a one-GPU box; bench.py --gpus N is the same code across NVLink)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    equal, frames = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert equal and frames == 5
