@@ -1,6 +1,7 @@
 """N>1 path: view sharding + frame gather.  CPU tier: world_size-2 gloo with a stub renderer (the collective plumbing and
 the shard arithmetic); GPU tier: two real scenes on one GPU emulate two ranks' blocks and are compared with a single
-launch over all views (a real 2-rank NCCL run needs two GPUs: bench.py --gpus 2)."""
+launch over all views, and two PROCESSES on one GPU run the fused peer-memory exchange through real CUDA IPC (a 2-rank NCCL run
+needs two GPUs: bench.py --gpus 2)."""
 import os
 import socket
 
