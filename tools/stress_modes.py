@@ -4,7 +4,8 @@
     python tools/stress_modes.py dirs [seed]   ordinary origins; one or two direction components shrunk by 1e-3 .. 1e-12 (not renormalised)
 
 Both compare colour, hit voxel and event counters for all four combinations and both forms (state machine, nested).  Round 1: no
-mismatch in either mode (seeds 1, 2).  The `dirs` mode is slow where the oracle has to execute the EPSILON crawls step by step."""
+mismatch in `ulps` (seeds 1, 2) nor in the part of `dirs` seed 1 that finished (terrain: all four combinations; shells: VCS + longest
+axis) -- `dirs` is slow where the oracle has to execute the EPSILON crawls step by step (hours for shells + original)."""
 import os, sys
 import numpy as np
 
