@@ -612,6 +612,25 @@ def test_render_from_region_corner_cameras(probe, storage, algo):
     s.close()
 
 
+def test_kernels_equal_their_host_compile_in_the_undefined_corner(probe):
+    """VCS + longest axis from the region-corner cameras: the reference's exists test is undefined at x = 64 there, so no oracle can
+    be matched -- but the kernels must still do exactly what their own source does when compiled for the host (tests/hostsim: same
+    headers, same guard padding): deterministic, inside the allocations, and identical between the state machine and the host."""
+    xyz, rgb = probe
+    po.set_lighting("sim")
+    sim, s = build_oracle("sim", xyz, rgb, "vcs"), build_product(xyz, rgb, "vcs")
+    po._lib("sim").sim_set_flat(1)
+    s.set_statistics(True)
+    for o, l in REGION_CORNER_CAMERAS:
+        cam = api.Camera(o, l, (0.0, 1.0, 0.0), 60.0, np.float32(320) / np.float32(180))
+        got = s.render(320, 180, "longestaxis", cam, scale=8, want_hits=True)
+        st = s.get_statistics()
+        want = sim.render(cam.data, 320, 180, "longestaxis", scale=8, want_counters=True)
+        assert np.array_equal(got["hits"], want["hits"]) and np.array_equal(got["rgb"], want["rgb"]), o
+        assert (st["exist_checks"], st["exist_false"], st["lookups"]) == tuple(int(v) for v in want["counters"][:3]), o
+    s.close()
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("algo", ["original", "longestaxis"])
 def test_trace_fuzz_from_grid_aligned_origins(algo):
