@@ -250,6 +250,24 @@ def test_core_scene_translation(storage, algo):
             assert np.array_equal(ra[k], rb[k]), (storage, algo, tr, k)
 
 
+@pytest.mark.parametrize("storage,algo", COMBOS)
+def test_core_origins_a_few_ulps_around_cluster_faces(storage, algo):
+    """Rays from origins whose coordinates sit a few ulps below / above a cluster face or an integer (tools/stress_modes.py `ulps` in
+    small): the first steps round differently on either side of such a value.  Colour, hit voxel and event counters."""
+    po.set_lighting("orc")
+    po.set_lighting("sim")
+    xyz, rgb = scenes.terrain(160, 77)
+    a, b = build_oracle("orc", xyz, rgb, storage), build_oracle("sim", xyz, rgb, storage)
+    f32 = np.float32
+    up, down = (lambda v: float(np.nextafter(f32(v), f32(np.inf)))), (lambda v: float(np.nextafter(f32(v), f32(-np.inf))))
+    origins = [(down(72.0), 150.0, up(up(40.0))), (up(16.0), down(down(down(136.0))), 81.0), (down(33.0), up(140.0), down(8.0))]
+    for i, org in enumerate(origins):
+        rays = scenes.random_rays(4000, org, seed=40 + i)
+        ta, tb = a.trace_rays(rays, algo, want_counters=True), b.trace_rays(rays, algo, want_counters=True)
+        for k in ("colour", "hits", "counters"):
+            assert np.array_equal(ta[k], tb[k]), (storage, algo, org, k)
+
+
 def coordinate64_rays():
     """Rays from (128, 64, 0) * 1/8 of the probe scene (scale 8): a corner shared by eight regions.  Their first EPSILON step leaves the
     region at -tiny on the two short axes and is rebased to exactly 64.0f, so the longest-axis walk tests voxels with a coordinate of 64
