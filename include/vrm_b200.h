@@ -76,9 +76,16 @@ int vrm_scene_reset_stream(vrm_scene* scene);
 int vrm_scene_synchronize(vrm_scene* scene);
 
 /* Append voxels in insertion order: xyz = n x 3 int32, rgb = n x uint32 (r<<16|g<<8|b).  Duplicate coordinates:
- * the last one added wins.  Coordinates must satisfy |c| < 2^23.  Legal only before vrm_scene_build. */
+ * the last one added wins.  Coordinates must satisfy |c| < 2^23.  Legal only before vrm_scene_build.
+ * The voxels go into ONE growable device array per scene (geometric growth, no allocation and no synchronisation per call);
+ * calls with few voxels are collected in a host block first and copied in blocks of 2^20.  The host variant may reuse its
+ * buffers on return.  The device variant enqueues its copy on the handle's stream: the source must stay valid until work
+ * ordered after the call on that stream runs (or until vrm_scene_synchronize). */
 int vrm_scene_add_voxels(vrm_scene* scene, const int32_t* xyz, const uint32_t* rgb, uint64_t n);
 int vrm_scene_add_voxels_device(vrm_scene* scene, const int32_t* d_xyz, const uint32_t* d_rgb, uint64_t n);
+/* VoxelSceneCPU::insertVoxel (geometry/VoxelSceneCPU.cuh:16-46), one voxel per call: a vector append on the host (see above),
+ * so the reference's insertion loops port as they are. */
+int vrm_scene_insert_voxel(vrm_scene* scene, int32_t x, int32_t y, int32_t z, uint32_t rgb);
 
 /* Procedural scenes generated ON THE GPU straight into the staging list (no host copy of the voxels; SURVEY.md 8f-3;
  * the reference's own generators are host loops calling insertVoxel: geometry/VoxelCube.cuh:10-39, VoxelSphere.cuh:10-66).
@@ -115,7 +122,11 @@ int vrm_make_unit_vector(const float v[3], float out[3]);
 
 /* Render one frame.  rgb_out = H x W x 3 bytes, row 0 = top (renderer/Renderer.cuh:1024-1031).
  * hits_out (nullable) = H x W x 4 int32: global voxel x,y,z of the first voxel the pixel's primary ray found and
- * a 0/1 flag.  kernel_ms (nullable) = device time of the render kernel alone. */
+ * a 0/1 flag.  kernel_ms (nullable) = device time of the render kernel alone.
+ * ALIGNMENT: hit records are written with 16-byte stores, so every DEVICE hit buffer (d_hits_out of the *_device entry
+ * points) must be 16-byte aligned -- VRM_ERR_INVALID otherwise.  Host buffers may have any alignment: a page-locked
+ * hits_out / rgb_out that is suitably aligned is written directly by the kernel, anything else goes through the handle's
+ * device buffers and a copy. */
 int vrm_render(vrm_scene* scene, const float camera[VRM_CAMERA_FLOATS], const float translation[3], uint32_t scale,
                int algorithm, uint32_t width, uint32_t height, uint8_t* rgb_out, int32_t* hits_out, float* kernel_ms);
 
@@ -181,6 +192,11 @@ int vrm_set_l2_persistence(vrm_scene* scene, int enabled);
  * (they are included in [0] and [1]).  Used for the roofline's algorithmic bytes. */
 int vrm_set_statistics(vrm_scene* scene, int enabled);
 int vrm_get_statistics(vrm_scene* scene, uint64_t out[8]);
+
+/* Measurement only (bench.py, tools/l2_bw.py): the device's L2 rates for an L2-resident working set of the given size -- 8-byte
+ * random gathers (loads per nanosecond and the algorithmic GB/s they amount to) and a coalesced streaming read.  These are the
+ * memory roofs of the traversal kernels, whose working set lives in L2; MEASURED_PEAKS.json only has the HBM copy rate. */
+int vrm_microbench_l2(int device, uint64_t working_set_bytes, float* gather8_loads_per_ns, float* gather8_gbs, float* stream_gbs);
 
 #ifdef __cplusplus
 }

@@ -312,9 +312,9 @@ int sim_scene_build(void* h, int storageType)
 		ri++;
 	}
 	// zeroed guard space, as in the product's builder: the reference can test a voxel with a coordinate of exactly 64 (undefined
-	// behaviour there) and the nested traversal then forms cluster ids of up to 575
-	s->headers.resize(s->headers.size() + 64 * 16, uint2{0, 0});
-	s->clusterMask.resize(s->clusterMask.size() + 16, 0u);
+	// behaviour there) and both forms of the traversal then form cluster ids of up to (8 << 6) | (8 << 3) | 8 = 584
+	s->headers.resize(s->headers.size() + 80 * 16, uint2{0, 0});
+	s->clusterMask.resize(s->clusterMask.size() + 32, 0u);
 	s->storage = storageType;
 	return 0;
 }

@@ -30,11 +30,11 @@ EMPTY = 1 << 30                                # EMPTY_KEY / EMPTY_VAL
 
 EXPORTS = [
     "vrm_error_string", "vrm_last_error", "vrm_device_available", "vrm_device_count", "vrm_device_name", "vrm_scene_create", "vrm_scene_destroy",
-    "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device",
+    "vrm_scene_set_stream", "vrm_scene_reset_stream", "vrm_scene_synchronize", "vrm_scene_add_voxels", "vrm_scene_add_voxels_device", "vrm_scene_insert_voxel",
     "vrm_scene_generate_terrain", "vrm_scene_generate_sparse_shells", "vrm_scene_generate_cube", "vrm_scene_generate_sphere",
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_render_views_device_strided", "vrm_render_views", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
-    "vrm_set_l2_persistence", "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device",
+    "vrm_set_l2_persistence", "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device", "vrm_microbench_l2",
 ]
 
 
@@ -68,6 +68,7 @@ def load_library():
         "vrm_scene_synchronize": (ci, [vp]),
         "vrm_scene_add_voxels": (ci, [vp, vp, vp, u64]),
         "vrm_scene_add_voxels_device": (ci, [vp, vp, vp, u64]),
+        "vrm_scene_insert_voxel": (ci, [vp, i32, i32, i32, u32]),
         "vrm_scene_generate_terrain": (ci, [vp, u32, u32, u32, C.POINTER(u64)]),
         "vrm_scene_generate_sparse_shells": (ci, [vp, u32, u32, u32, u32, C.POINTER(u64)]),
         "vrm_scene_generate_cube": (ci, [vp, i32, i32, i32, i32, C.POINTER(u64)]),
@@ -93,6 +94,7 @@ def load_library():
         "vrm_set_l2_persistence": (ci, [vp, ci]),
         "vrm_set_statistics": (ci, [vp, ci]),
         "vrm_get_statistics": (ci, [vp, vp]),
+        "vrm_microbench_l2": (ci, [ci, u64, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -104,6 +106,15 @@ def load_library():
 
 def device_available() -> bool:
     return bool(load_library().vrm_device_available())
+
+
+def microbench_l2(device: int = 0, working_set_bytes: int = 32 << 20):
+    """L2 roofs for an L2-resident working set: dict(gather8_loads_per_ns, gather8_gbs, stream_gbs).  Measurement only."""
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    rc = load_library().vrm_microbench_l2(device, working_set_bytes, C.byref(a), C.byref(b), C.byref(c))
+    if rc:
+        raise VrmError(f"vrm_microbench_l2 failed: {rc}")
+    return dict(working_set_bytes=working_set_bytes, gather8_loads_per_ns=a.value, gather8_gbs=b.value, stream_gbs=c.value)
 
 
 def _ptr(a):
@@ -186,7 +197,10 @@ class VoxelScene:
 
     # -- scene construction --------------------------------------------------------------------------------------
     def insert_voxel(self, x: int, y: int, z: int, color: int):
-        self.add_voxels(np.array([[x, y, z]], np.int32), np.array([color], np.uint32))
+        """``VoxelSceneCPU::insertVoxel``: one voxel per call (collected on the host by the library, no device work per call)."""
+        rc = self.lib.vrm_scene_insert_voxel(self.h, x, y, z, color)
+        if rc:
+            self._check(rc, "vrm_scene_insert_voxel")
 
     def add_voxels(self, xyz, rgb):
         xyz = np.ascontiguousarray(xyz, np.int32).reshape(-1, 3)

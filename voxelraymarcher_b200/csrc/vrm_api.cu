@@ -85,16 +85,19 @@ int check_render_args(vrm_scene* s, const float* camera, const float* translatio
 int upload_cameras(vrm_scene* s, const float* cameras, uint32_t nViews)
 {
 	size_t bytes = (size_t)nViews * VRM_CAMERA_FLOATS * sizeof(float);
-	if (s->camsBytes < bytes)
+	if (s->camsBytes < bytes || !s->h_cams || !s->d_cams)
 	{
-		VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+		// grow: the new pair is allocated first and swapped in only when both allocations succeeded, so a failure leaves the
+		// handle as it was (status return, no half-updated state)
+		float* nh = nullptr; float* nd = nullptr;
+		if (cudaMallocHost(&nh, bytes) != cudaSuccess) { cudaGetLastError(); s->lastError = "camera staging allocation failed"; return VRM_ERR_NOMEM; }
+		cudaError_t e = cudaMalloc(&nd, bytes);
+		if (e != cudaSuccess) { cudaFreeHost(nh); return vrm_fail_cuda(s, e, "camera buffer allocation"); }
+		e = cudaStreamSynchronize(s->stream);  // the old pair may still be in flight
+		if (e != cudaSuccess) { cudaFreeHost(nh); cudaFree(nd); return vrm_fail_cuda(s, e, "cudaStreamSynchronize"); }
 		if (s->h_cams) cudaFreeHost(s->h_cams);
-		s->h_cams = nullptr;
-		VRM_CUDA(s, cudaMallocHost(&s->h_cams, bytes));
-		void* p = s->d_cams; size_t have = s->camsBytes;
-		int rc = ensure(s, &p, &have, bytes);
-		s->d_cams = static_cast<float*>(p); s->camsBytes = have;
-		if (rc) return rc;
+		if (s->d_cams) cudaFree(s->d_cams);
+		s->h_cams = nh; s->d_cams = nd; s->camsBytes = bytes;
 	}
 	else
 	{
@@ -169,6 +172,7 @@ int vrm_scene_create(int device, vrm_scene** out)
 	s->light.pos[0] = 10.0f; s->light.pos[1] = 10.0f; s->light.pos[2] = -10.0f;
 	s->light.usePoint = 0; s->light.useShadows = 1;
 	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess) vrm_configure_pool(device);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->ownStream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
@@ -192,8 +196,10 @@ int vrm_scene_destroy(vrm_scene* s)
 	if (!s) return VRM_OK;
 	cudaSetDevice(s->device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
-	for (VoxelChunk& c : s->chunks) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); }
+	vrm_stage_free(s);
+	vrm_free_async(s, s->d_regionMinMax); s->d_regionMinMax = nullptr;
 	vrm_free_structure(s);
+	cudaStreamSynchronize(s->stream);
 	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer);
 	if (s->h_cams) cudaFreeHost(s->h_cams);
 	if (s->ev0) cudaEventDestroy(s->ev0);
@@ -240,26 +246,56 @@ int vrm_scene_synchronize(vrm_scene* s)
 	return VRM_OK;
 }
 
-static int add_voxels(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n, cudaMemcpyKind kind)
+static int add_voxels(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n, bool fromDevice)
 {
 	if (!s || (n && (!xyz || !rgb))) return VRM_ERR_INVALID;
 	if (s->storage >= 0) { s->lastError = "scene already built"; return VRM_ERR_STATE; }
 	if (n == 0) return VRM_OK;
+	if (!fromDevice && n <= kPendingMaxCall)
+	{
+		// short host calls (down to the reference's one voxel per insertVoxel call) are collected on the host
+		try
+		{
+			s->pendingXyz.insert(s->pendingXyz.end(), xyz, xyz + n * 3);
+			s->pendingRgb.insert(s->pendingRgb.end(), rgb, rgb + n);
+		}
+		catch (...) { s->lastError = "host staging allocation failed"; return VRM_ERR_NOMEM; }
+		if (s->pendingRgb.size() < kPendingFlushVoxels) return VRM_OK;
+		VRM_CUDA(s, cudaSetDevice(s->device));
+		return vrm_stage_flush_pending(s);
+	}
 	VRM_CUDA(s, cudaSetDevice(s->device));
-	VoxelChunk c = {nullptr, nullptr, n};
-	cudaError_t e = cudaMalloc(&c.d_xyz, n * 3 * sizeof(int32_t));
-	if (e == cudaSuccess) e = cudaMalloc(&c.d_rgb, n * sizeof(uint32_t));
-	if (e == cudaSuccess) e = cudaMemcpyAsync(c.d_xyz, xyz, n * 3 * sizeof(int32_t), kind, s->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(c.d_rgb, rgb, n * sizeof(uint32_t), kind, s->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);  // the caller may reuse its buffers on return
-	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_add_voxels"); }
-	s->chunks.push_back(c);
-	s->nStaged += n;
+	int32_t* dx = nullptr; uint32_t* dr = nullptr;
+	int rc = vrm_stage_reserve(s, n, &dx, &dr);
+	if (rc) return rc;
+	const cudaMemcpyKind kind = fromDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	VRM_CUDA(s, cudaMemcpyAsync(dx, xyz, n * 3 * sizeof(int32_t), kind, s->stream));
+	VRM_CUDA(s, cudaMemcpyAsync(dr, rgb, n * sizeof(uint32_t), kind, s->stream));
+	rc = vrm_stage_commit(s, n);
+	if (rc) return rc;
+	if (!fromDevice)
+	{
+		// "The caller may reuse its buffers on return": a copy from pageable memory has been staged by the driver when
+		// cudaMemcpyAsync returns; only page-locked sources are read asynchronously and need the wait.
+		cudaPointerAttributes at;
+		const bool pinned = cudaPointerGetAttributes(&at, xyz) == cudaSuccess && at.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		cudaPointerAttributes at2;
+		const bool pinned2 = cudaPointerGetAttributes(&at2, rgb) == cudaSuccess && at2.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		if (pinned || pinned2) VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	}
 	return VRM_OK;
 }
 
-int vrm_scene_add_voxels(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n) { return add_voxels(s, xyz, rgb, n, cudaMemcpyHostToDevice); }
-int vrm_scene_add_voxels_device(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n) { return add_voxels(s, xyz, rgb, n, cudaMemcpyDeviceToDevice); }
+int vrm_scene_add_voxels(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n) { return add_voxels(s, xyz, rgb, n, false); }
+int vrm_scene_add_voxels_device(vrm_scene* s, const int32_t* xyz, const uint32_t* rgb, uint64_t n) { return add_voxels(s, xyz, rgb, n, true); }
+
+int vrm_scene_insert_voxel(vrm_scene* s, int32_t x, int32_t y, int32_t z, uint32_t rgb)
+{
+	const int32_t xyz[3] = {x, y, z};
+	return add_voxels(s, xyz, &rgb, 1, false);
+}
 
 int vrm_scene_build(vrm_scene* s, int storage_type, float* build_ms)
 {
@@ -269,9 +305,9 @@ int vrm_scene_build(vrm_scene* s, int storage_type, float* build_ms)
 	int rc = vrm_build_structure(s, storage_type, build_ms);
 	if (rc == VRM_OK)
 	{
-		// the staged copies are no longer needed
-		for (VoxelChunk& c : s->chunks) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); }
-		s->chunks.clear();
+		// the staged copies are no longer needed (the colour array may have moved into the structure: vrm_build.cu)
+		vrm_stage_free(s);
+		s->nStaged = 0;
 	}
 	return rc;
 }
@@ -339,6 +375,7 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 	};
 	uint8_t* d_rgb = static_cast<uint8_t*>(device_alias(rgb_out));
 	int32_t* d_hits = hits_out ? static_cast<int32_t*>(device_alias(hits_out)) : nullptr;
+	if (d_hits && (reinterpret_cast<uintptr_t>(d_hits) & 15u)) d_hits = nullptr;  // hit records are 16-byte stores: an unaligned page-locked buffer takes the copy path
 	const bool copyRgb = d_rgb == nullptr, copyHits = hits_out && d_hits == nullptr;
 	void* p;
 	if (copyRgb) { p = s->d_fb; rc = ensure(s, &p, &s->fbBytes, px * 3); s->d_fb = static_cast<uint8_t*>(p); if (rc) return rc; d_rgb = s->d_fb; }

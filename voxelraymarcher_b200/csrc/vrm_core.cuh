@@ -297,6 +297,9 @@ VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mul
 #ifndef VRM_COORD64_EMPTY
 #define VRM_COORD64_EMPTY 1
 #endif
+#ifndef VRM_NESTED_TWO_PHASE
+#define VRM_NESTED_TWO_PHASE 1  // nested traversal (march_scene): primary rays of a warp first, then its shadow rays together
+#endif
 #ifndef VRM_HASH_CLUSTER_FILTER
 #define VRM_HASH_CLUSTER_FILTER 1
 #endif
@@ -1060,6 +1063,39 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 	RayDir ko = k;
 	if constexpr (ALGO != kAlgoOriginal) ko = scaled_raydir(k);
 	int32_t ri = region_entry(c, p, reg);
+#if VRM_NESTED_TWO_PHASE
+	// Two phases: every lane first marches its PRIMARY ray to a hit or out of the scene -- the loop below has one exit, so the warp
+	// reconverges behind it -- and only then do the lanes that hit shade and walk their shadow rays, together.  Executed as the
+	// reference nests it (shadow march inside the hit branch inside the region loop) the shadow rays of a warp ran one hit time after
+	// the other: 11.9 of 32 threads active in the shadow half of the hash table kernels (profiles/r01j).  Same operations per ray.
+	uint32_t col = kEmpty;
+	HitInfo h;
+	while (ri != -2)
+	{
+		ri = skip_null_regions<ST, STATS, P, false>(c, p, o, k, reg, ri);
+		if (ri == -2) break;
+		RegionRef<ST> r = load_region<ST>(c.sv, ri);
+		if constexpr (ALGO == kAlgoOriginal) col = march_original<ST, STATS, P>(c, r, p, o, k, reg, h);
+		else col = march_longest_axis<ST, STATS, false>(c, r, p, o, k, ko, reg, h);
+		if (col != kEmpty) break;
+		rebase_region(o, reg);
+		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
+	}
+	uint32_t lit = 0;
+	if (col != kEmpty)
+	{
+		// applyLighting(...) * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion)  (Renderer.cuh:314-315,821-822,...)
+		float hitW[3];
+		int regW[3];
+		to_world(p, h.pos, hitW); to_world(p, reg, regW);
+		lit = apply_lighting(c.light, c.translation, col, h.nAxisW, h.nSign, hitW, regW);
+		bool shadowed;
+		if constexpr (ALGO == kAlgoOriginal) shadowed = in_shadow<ST, STATS, false>(c, hitW, regW);
+		else shadowed = h.laShadow ? in_shadow<ST, STATS, true>(c, hitW, regW) : in_shadow<ST, STATS, false>(c, hitW, regW);
+		lit *= (uint32_t)!shadowed;
+	}
+	return lit;
+#else
 	while (ri != -2)
 	{
 		ri = skip_null_regions<ST, STATS, P, false>(c, p, o, k, reg, ri);
@@ -1085,6 +1121,7 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
 	}
 	return 0;
+#endif
 }
 
 // calculateWorldRay (Renderer.cuh:1013-1022) + Camera::generateRay (Camera.cuh:25-29).  cam = 15 floats.

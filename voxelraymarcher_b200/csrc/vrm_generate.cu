@@ -218,15 +218,6 @@ int scan_counts(vrm_scene* s, const uint32_t* counts, uint32_t* starts, uint64_t
 	return VRM_OK;
 }
 
-int stage_chunk(vrm_scene* s, uint64_t total, VoxelChunk* c)
-{
-	c->d_xyz = nullptr; c->d_rgb = nullptr; c->n = total;
-	cudaError_t e = cudaMalloc(&c->d_xyz, total * 3 * sizeof(int32_t));
-	if (e == cudaSuccess) e = cudaMalloc(&c->d_rgb, total * sizeof(uint32_t));
-	if (e != cudaSuccess) { cudaFree(c->d_xyz); cudaFree(c->d_rgb); return vrm_fail_cuda(s, e, "scene generator allocation"); }
-	return VRM_OK;
-}
-
 int check_generate(vrm_scene* s)
 {
 	if (!s) return VRM_ERR_INVALID;
@@ -257,15 +248,13 @@ int vrm_scene_generate_terrain(vrm_scene* s, uint32_t size, uint32_t seed, uint3
 	rc = scan_counts(s, heights.as<uint32_t>(), starts.as<uint32_t>(), cols, &total);
 	if (rc) return rc;
 	if (total >= (1ull << 32)) { s->lastError = "terrain has more than 2^32 voxels"; return VRM_ERR_INVALID; }
-	VoxelChunk c;
-	rc = stage_chunk(s, total, &c);
+	int32_t* d_xyz = nullptr; uint32_t* d_rgb = nullptr;
+	rc = vrm_stage_reserve(s, total, &d_xyz, &d_rgb);  // appended to the scene's staging arrays, in insertion order
 	if (rc) return rc;
-	terrain_fill_kernel<<<grid_for(total), kThreads, 0, s->stream>>>(size, starts.as<uint32_t>(), total, c.d_xyz, c.d_rgb);
-	cudaError_t e = cudaGetLastError();
-	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_terrain"); }
-	s->chunks.push_back(c);
-	s->nStaged += total;
+terrain_fill_kernel<<<grid_for(total), kThreads, 0, s->stream>>>(size, starts.as<uint32_t>(), total, d_xyz, d_rgb);
+	VRM_CUDA(s, cudaGetLastError());
+	rc = vrm_stage_commit(s, total);
+	if (rc) return rc;
 	if (n_out) *n_out = total;
 	return VRM_OK;
 }
@@ -276,15 +265,13 @@ int vrm_scene_generate_cube(vrm_scene* s, int32_t x, int32_t y, int32_t z, int32
 	if (rc) return rc;
 	if (half_width < 1 || half_width > 4096) { s->lastError = "cube half width must be in [1, 4096]"; return VRM_ERR_INVALID; }
 	const uint64_t w = 2ull * (uint64_t)half_width, total = 6ull * w * w;
-	VoxelChunk c;
-	rc = stage_chunk(s, total, &c);
+	int32_t* d_xyz = nullptr; uint32_t* d_rgb = nullptr;
+	rc = vrm_stage_reserve(s, total, &d_xyz, &d_rgb);  // appended to the scene's staging arrays, in insertion order
 	if (rc) return rc;
-	cube_kernel<<<grid_for(total), kThreads, 0, s->stream>>>(x, y, z, half_width, c.d_xyz, c.d_rgb);
-	cudaError_t e = cudaGetLastError();
-	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_cube"); }
-	s->chunks.push_back(c);
-	s->nStaged += total;
+cube_kernel<<<grid_for(total), kThreads, 0, s->stream>>>(x, y, z, half_width, d_xyz, d_rgb);
+	VRM_CUDA(s, cudaGetLastError());
+	rc = vrm_stage_commit(s, total);
+	if (rc) return rc;
 	if (n_out) *n_out = total;
 	return VRM_OK;
 }
@@ -306,15 +293,13 @@ int vrm_scene_generate_sphere(vrm_scene* s, uint32_t x, uint32_t y, uint32_t z, 
 	rc = scan_counts(s, flags.as<uint32_t>(), pos.as<uint32_t>(), candidates, &total);
 	if (rc) return rc;
 	if (total == 0) { if (n_out) *n_out = 0; return VRM_OK; }
-	VoxelChunk c;
-	rc = stage_chunk(s, total, &c);
+	int32_t* d_xyz = nullptr; uint32_t* d_rgb = nullptr;
+	rc = vrm_stage_reserve(s, total, &d_xyz, &d_rgb);  // appended to the scene's staging arrays, in insertion order
 	if (rc) return rc;
-	sphere_fill_kernel<<<grid_for(candidates), kThreads, 0, s->stream>>>(x, y, z, radius, step, candidates, pos.as<uint32_t>(), c.d_xyz, c.d_rgb);
-	cudaError_t e = cudaGetLastError();
-	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_sphere"); }
-	s->chunks.push_back(c);
-	s->nStaged += total;
+sphere_fill_kernel<<<grid_for(candidates), kThreads, 0, s->stream>>>(x, y, z, radius, step, candidates, pos.as<uint32_t>(), d_xyz, d_rgb);
+	VRM_CUDA(s, cudaGetLastError());
+	rc = vrm_stage_commit(s, total);
+	if (rc) return rc;
 	if (n_out) *n_out = total;
 	return VRM_OK;
 }
@@ -338,15 +323,13 @@ int vrm_scene_generate_sparse_shells(vrm_scene* s, uint32_t size, uint32_t cell,
 	if (rc) return rc;
 	if (total >= (1ull << 32)) { s->lastError = "sparse_shells has more than 2^32 voxels"; return VRM_ERR_INVALID; }
 	if (total == 0) { if (n_out) *n_out = 0; return VRM_OK; }
-	VoxelChunk c;
-	rc = stage_chunk(s, total, &c);
+	int32_t* d_xyz = nullptr; uint32_t* d_rgb = nullptr;
+	rc = vrm_stage_reserve(s, total, &d_xyz, &d_rgb);  // appended to the scene's staging arrays, in insertion order
 	if (rc) return rc;
-	shell_fill_kernel<<<(unsigned)cells, kThreads, 0, s->stream>>>(n, cell, seed, fill_pct, starts.as<uint32_t>(), c.d_xyz, c.d_rgb);
-	cudaError_t e = cudaGetLastError();
-	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-	if (e != cudaSuccess) { cudaFree(c.d_xyz); cudaFree(c.d_rgb); return vrm_fail_cuda(s, e, "vrm_scene_generate_sparse_shells"); }
-	s->chunks.push_back(c);
-	s->nStaged += total;
+shell_fill_kernel<<<(unsigned)cells, kThreads, 0, s->stream>>>(n, cell, seed, fill_pct, starts.as<uint32_t>(), d_xyz, d_rgb);
+	VRM_CUDA(s, cudaGetLastError());
+	rc = vrm_stage_commit(s, total);
+	if (rc) return rc;
 	if (n_out) *n_out = total;
 	return VRM_OK;
 }

@@ -8,12 +8,11 @@
 
 #include "vrm_core.cuh"
 
-struct VoxelChunk
-{
-	int32_t* d_xyz;
-	uint32_t* d_rgb;
-	uint64_t n;
-};
+// Small inserts (vrm_scene_insert_voxel, short vrm_scene_add_voxels calls) are collected on the host and reach the device in
+// blocks of this many voxels: a caller porting the reference's insertVoxel loop (VoxelSceneCPU.cuh:16-46) pays a vector append per
+// voxel, not a device allocation and a stream synchronisation.
+constexpr uint64_t kPendingFlushVoxels = 1ull << 20;
+constexpr uint64_t kPendingMaxCall = 1ull << 14;  // calls with more voxels than this go to the device directly
 
 struct vrm_scene
 {
@@ -22,9 +21,15 @@ struct vrm_scene
 	cudaStream_t stream = nullptr;
 	std::string lastError;
 
-	// staged voxels (insertion order)
-	std::vector<VoxelChunk> chunks;
-	uint64_t nStaged = 0;
+	// staged voxels, in insertion order: ONE growable pair of device arrays (geometric growth, stream-ordered allocation) ...
+	int32_t* d_stageXyz = nullptr;   // [stageCap][3]
+	uint32_t* d_stageRgb = nullptr;  // [stageCap]
+	uint64_t stageCap = 0;
+	uint64_t nStaged = 0;            // voxels in the device arrays
+	int* d_regionMinMax = nullptr;   // running {min, max} region coordinate of everything staged on the device (VoxelSceneCPU.cuh:28-35)
+	// ... behind a host-side block of voxels that have not been copied yet (kPendingFlushVoxels)
+	std::vector<int32_t> pendingXyz;
+	std::vector<uint32_t> pendingRgb;
 
 	// built structure
 	int storage = -1;
@@ -91,6 +96,18 @@ int vrm_fail_cuda(vrm_scene* s, cudaError_t e, const char* what);
 // vrm_build.cu
 int vrm_build_structure(vrm_scene* s, int storageType, float* buildMs);
 void vrm_free_structure(vrm_scene* s);
+// Staging (vrm_build.cu).  vrm_stage_reserve: flush the host block, make room for `extra` more voxels and return where they go;
+// the caller fills them on s->stream (copy or kernel) and then calls vrm_stage_commit, which folds them into the running region
+// extent.  Nothing here synchronises the stream.
+int vrm_stage_reserve(vrm_scene* s, uint64_t extra, int32_t** d_xyz, uint32_t** d_rgb);
+int vrm_stage_commit(vrm_scene* s, uint64_t n);
+int vrm_stage_flush_pending(vrm_scene* s);
+void vrm_stage_free(vrm_scene* s);
+// stream-ordered allocation from the device's default memory pool (release threshold raised so that freed scratch is reused by
+// the next build instead of going back to the driver)
+cudaError_t vrm_alloc_async(vrm_scene* s, void** p, size_t bytes);
+void vrm_free_async(vrm_scene* s, void* p);
+void vrm_configure_pool(int device);
 size_t vrm_scan_scratch_elems(uint64_t n);  // uint32 elements of scratch an exclusive scan of n elements needs
 void vrm_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st);  // out may alias in
 

@@ -578,7 +578,9 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	a.tilesX = (W + kTileW - 1) / kTileW;
 	a.tilesPerView = a.tilesX * ((H + kTileH - 1) / kTileH);
 	a.nViews = nViews;
-	if ((uint64_t)a.tilesPerView * nViews * 32ull >= (1ull << 32)) { s->lastError = "too many pixels for one launch"; return VRM_ERR_INVALID; }
+	// 32-bit pixel-slot numbers exist only in the persistent debug kernel (VRM_RENDER_MODE=0); the tiled kernels index with size_t
+	if (s->renderMode == 0 && (uint64_t)a.tilesPerView * nViews * 32ull >= (1ull << 32)) { s->lastError = "too many pixels for one launch of the persistent kernel"; return VRM_ERR_INVALID; }
+	if (d_hits && (reinterpret_cast<uintptr_t>(d_hits) & 15u)) { s->lastError = "hit buffer must be 16-byte aligned"; return VRM_ERR_INVALID; }
 	if (s->statsEnabled && yBase == 0)
 	{
 		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
@@ -598,6 +600,7 @@ int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float*
                      uint32_t* d_colour, int32_t* d_hits)
 {
 	if (n == 0) return VRM_OK;
+	if (d_hits && (reinterpret_cast<uintptr_t>(d_hits) & 15u)) { s->lastError = "hit buffer must be 16-byte aligned"; return VRM_ERR_INVALID; }
 	vrm_apply_l2_window(s);
 	TraceArgs a;
 	fill_common(a, s, translation, scale);
