@@ -17,6 +17,7 @@ struct uint4 { uint32_t x, y, z, w; };
 
 #include "../../voxelraymarcher_b200/csrc/vrm_core.cuh"
 #include "../../voxelraymarcher_b200/csrc/vrm_flat.cuh"
+#include "../../voxelraymarcher_b200/csrc/vrm_lean.cuh"
 
 using namespace vrm;
 
@@ -48,11 +49,22 @@ struct SimScene
 
 Lighting gLight = {{0.57735026f, 0.57735026f, 0.57735026f}, {1, 1, 1}, {10, 10, -10}, 0, 1};
 unsigned long long gCrawlSkipped = 0;  // cluster-skip iterations fast-forwarded by crawl_skip (render calls only)
-int gFlat = 1;  // 1: the flat state machine of vrm_flat.cuh (what the render kernels run); 0: the nested form of vrm_core.cuh
+int gFlat = 1;  // 1: the flat state machine of vrm_flat.cuh; 0: the nested form of vrm_core.cuh; 2: the lean machine of vrm_lean.cuh (what the hot render kernels run)
+unsigned long long gLeanParked = 0;  // rays the lean machine handed to the generic one (mode 2)
 
 template <int ST, int ALGO>
 uint32_t march(RayCtx<ST, true>& c, const float* o, const float* d, float scale)
 {
+	if (gFlat == 2)
+	{
+		Vec4 kc[kKcVectors];
+		LeanRay<ST, ALGO, true, 1> ray;
+		if (march_scene_lean<ST, ALGO, true, 1>(c, kc, o, d, scale, ray)) return ray.result;
+		// parked: the ray is re-traced from its start by the generic machine, as resume_kernel does (vrm_render.cu)
+		#pragma omp atomic
+		gLeanParked++;
+		c.reset();
+	}
 	return gFlat ? march_scene_flat<ST, ALGO, true>(c, o, d, scale) : march_scene<ST, ALGO, true>(c, o, d, scale);
 }
 
@@ -131,6 +143,7 @@ void trace(const SimScene& s, const float* rays, uint64_t n, const float* tr, fl
 extern "C" {
 
 void sim_set_flat(int flat) { gFlat = flat; }
+unsigned long long sim_lean_parked() { unsigned long long v = gLeanParked; gLeanParked = 0; return v; }
 int sim_is_flat() { return gFlat; }
 
 // crawl_skip against the literal iterations it replaces: pseudo-random positions (many of them exactly on cluster faces, integers and

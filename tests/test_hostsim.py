@@ -7,10 +7,14 @@ import pytest
 from tests.common import COMBOS, MINI_CAMERAS, PROBE_CAMERAS, build_oracle, camera, lookup_queries, oracle_kind, po, scenes
 
 
-@pytest.fixture(params=["nested", "flat"], autouse=True)
+FORMS = {"nested": 0, "flat": 1, "lean": 2}
+
+
+@pytest.fixture(params=list(FORMS), autouse=True)
 def traversal_form(request):
-    """Both forms of the traversal the kernels are built from: vrm_core.cuh (nested loops) and vrm_flat.cuh (state machine)."""
-    po._lib("sim").sim_set_flat(1 if request.param == "flat" else 0)
+    """The three forms of the traversal the kernels are built from: vrm_core.cuh (nested loops), vrm_flat.cuh (generic state
+    machine) and vrm_lean.cuh (the hot kernels' state machine; rays it parks are re-traced by the generic one, as on the GPU)."""
+    po._lib("sim").sim_set_flat(FORMS[request.param])
     yield request.param
     po._lib("sim").sim_set_flat(1)
 

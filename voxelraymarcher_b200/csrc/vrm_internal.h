@@ -62,8 +62,12 @@ struct vrm_scene
 
 	unsigned int* d_queue = nullptr;  // persistent render kernel: next unclaimed pixel slot
 	void* d_defer = nullptr;          // rays parked for resume_kernel (vrm_render.cu): DeferHeader + records
+	// lean kernels (vrm_lean.cuh): one bit per ray of a launch for rays that need a slow path + {count, blocks done}; the resume kernel
+	// re-traces the flagged rays with the generic machine and leaves both all-zero again
+	uint32_t* d_parkBits = nullptr;   size_t parkWords = 0;
+	unsigned int* d_parkCtl = nullptr;
 	int numSms = 148;
-	int renderMode = -1;              // -1 = per-combination default (vrm_render.cu); 0 = scheduled persistent kernel, 1 = nested loops, 2 = per-lane state machine (VRM_RENDER_MODE)
+	int renderMode = -1;              // -1 = per-combination default (vrm_render.cu); 0 = scheduled persistent kernel, 1 = nested loops, 2 = generic per-lane state machine, 3 = lean state machine (VRM_RENDER_MODE)
 
 	// L2 access-policy window over the structure's hottest array (vrm_set_l2_persistence / VRM_L2_PERSIST=1; off by default:
 	// measured no gain on the BASELINE scenes, whose touched working set already lives in L1/L2 -- DESIGN.md 3.2)

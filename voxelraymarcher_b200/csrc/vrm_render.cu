@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #include "vrm_flat.cuh"
+#include "vrm_lean.cuh"
 #include "../../include/vrm_b200.h"
 
 using namespace vrm;
@@ -65,6 +66,8 @@ struct RenderArgs
 	void* defer;        // DeferHeader + records: rays parked for resume_kernel (vrm_flat.cuh kPpDefer)
 	unsigned int* queue;   // persistent kernel: next unclaimed pixel slot
 	uint32_t tilesX, tilesPerView, nViews;
+	uint32_t* parkBits;    // lean kernels: one bit per ray (index (view * H + y) * W + x) that must be re-traced by resume_lean_kernel
+	unsigned int* parkCtl; // {parked rays, resume blocks done}
 };
 
 template <bool STATS, int ST>
@@ -367,6 +370,8 @@ struct TraceArgs
 	int32_t* hits;
 	Stats* stats;
 	void* defer;
+	uint32_t* parkBits;    // lean kernels: one bit per ray that must be re-traced by resume_lean_trace_kernel
+	unsigned int* parkCtl;
 };
 
 // Incoherent rays are latency-bound: occupancy is worth more than a few spilled registers (measured, 1024^3 shells, 8.3 M rays:
@@ -433,6 +438,179 @@ __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MI
 	flush_stats<STATS>(c, a.stats);
 }
 
+
+// ---- lean state machine (vrm_lean.cuh) ------------------------------------------------------------------------------------------
+// Same tile mapping and staged stores as render_kernel; per-ray constants in shared memory ([vector][thread]); rays that need a
+// slow path flag themselves in a bitmap and are re-traced by resume_lean_kernel.
+#ifndef VRM_LEAN_MINBLOCKS
+#define VRM_LEAN_MINBLOCKS 4
+#endif
+__device__ __forceinline__ void park_ray(uint32_t* bits, unsigned int* ctl, unsigned long long rayIndex)
+{
+	atomicOr(bits + (rayIndex >> 5), 1u << (unsigned)(rayIndex & 31ull));
+	atomicAdd(ctl, 1u);
+}
+
+template <int ST, int ALGO>
+__global__ void __launch_bounds__(kRenderThreads, VRM_LEAN_MINBLOCKS * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_lean_kernel(const RenderArgs a)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t lx = (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1)), ly = (warp / kBlockTilesX) * kTileH + (lane / kTileW);
+	const uint32_t x0 = blockIdx.x * kBlockW, y0 = a.yBase + blockIdx.y * kBlockH;
+	const uint32_t x = x0 + lx, y = y0 + ly;
+	const bool inside = x < a.W && y < a.yEnd;
+	__shared__ uint32_t staged[kBlockH][kBlockW * 3 / 4];
+	__shared__ Vec4 consts[kKcVectors][kRenderThreads];
+	Vec4* kc = &consts[0][threadIdx.x];
+	RayCtx<ST, false> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
+	if (inside)
+	{
+		const float* cam = a.cams + (size_t)blockIdx.z * 15;
+		float camv[15];
+#pragma unroll
+		for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+		primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
+		if (a.hits)
+		{
+			c.hitOut = a.hits + 4 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x);
+			*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+		}
+	}
+	LeanRay<ST, ALGO, false, kRenderThreads> ray;
+	const bool finished = march_scene_lean_warp<ST, ALGO, false, kRenderThreads>(c, kc, inside, o, d, a.scale, ray);
+	if (!finished) park_ray(a.parkBits, a.parkCtl, ((unsigned long long)blockIdx.z * a.H + y) * a.W + x);
+	const uint32_t color = ray.result;
+	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
+	const bool wholeBlock = x0 + kBlockW <= a.W && y0 + kBlockH <= a.yEnd && a.rowWordsOk;
+	if (wholeBlock)
+	{
+		uint8_t* sb = reinterpret_cast<uint8_t*>(&staged[ly][0]) + lx * 3;
+		sb[0] = (uint8_t)(color >> 16); sb[1] = (uint8_t)((color >> 8) & 0xFF); sb[2] = (uint8_t)(color & 0xFF);
+		__syncthreads();
+		if (threadIdx.x < kBlockH * (kBlockW * 3 / 4))
+		{
+			const uint32_t row = threadIdx.x / (kBlockW * 3 / 4), w = threadIdx.x % (kBlockW * 3 / 4);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.viewPixels + (size_t)(y0 + row) * a.W + x0) * 3);
+			dst[w] = staged[row][w];
+		}
+	}
+	else if (inside)
+	{
+		size_t p = (size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x;
+		a.rgb[3 * p] = (uint8_t)(color >> 16);
+		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
+		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
+	}
+}
+
+constexpr int kLeanTraceThreads = 128;
+template <int ST, int ALGO>
+__global__ void __launch_bounds__(kLeanTraceThreads, VRM_LEAN_MINBLOCKS) trace_lean_kernel(const TraceArgs a)
+{
+	const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	__shared__ Vec4 consts[kKcVectors][kLeanTraceThreads];
+	Vec4* kc = &consts[0][threadIdx.x];
+	if (i >= a.n) return;
+	RayCtx<ST, false> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	const float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
+	const float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
+	if (a.hits)
+	{
+		c.hitOut = a.hits + 4 * i;
+		*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+	}
+	LeanRay<ST, ALGO, false, kLeanTraceThreads> ray;
+	const bool finished = march_scene_lean<ST, ALGO, false, kLeanTraceThreads>(c, kc, o, d, a.scale, ray);
+	if (!finished) park_ray(a.parkBits, a.parkCtl, i);
+	a.colour[i] = ray.result;
+}
+
+// The rays the lean kernels flagged, re-traced from their start by the generic state machine (all slow paths, fast-forwards in
+// place).  One warp per bitmap word, one lane per bit.  The last block to finish leaves the bitmap counters zero for the next launch
+// (every set bit is cleared by the warp that handles it).
+constexpr int kResumeLeanThreads = 256;
+template <int ST, int ALGO, bool RENDER, class Args>
+__global__ void __launch_bounds__(kResumeLeanThreads) resume_lean_kernel(const Args a, unsigned long long totalRays)
+{
+	__shared__ unsigned int parked;
+	if (threadIdx.x == 0) parked = *reinterpret_cast<volatile unsigned int*>(a.parkCtl);
+	__syncthreads();
+	if (parked != 0u)
+	{
+		const unsigned lane = threadIdx.x & 31u;
+		const unsigned long long words = (totalRays + 31ull) >> 5;
+		const unsigned long long warpsTotal = (unsigned long long)gridDim.x * (kResumeLeanThreads / 32);
+		RayCtx<ST, false> c;
+		c.sv = a.sv;
+		c.light = a.light;
+		c.lw = a.lw;
+		c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+		for (unsigned long long w = (unsigned long long)blockIdx.x * (kResumeLeanThreads / 32) + (threadIdx.x >> 5); w < words; w += warpsTotal)
+		{
+			const uint32_t bits = a.parkBits[w];
+			if (bits == 0u) continue;
+			__syncwarp();
+			if (lane == 0) a.parkBits[w] = 0u;
+			if (!((bits >> lane) & 1u)) continue;
+			const unsigned long long idx = (w << 5) | lane;
+			c.reset();
+			c.hitOut = nullptr;
+			float o[3], d[3];
+			uint32_t colour;
+			int unused;
+			if constexpr (RENDER)
+			{
+				const unsigned long long perView = (unsigned long long)a.W * a.H;
+				const uint32_t view = (uint32_t)(idx / perView);
+				const unsigned long long rem = idx - (unsigned long long)view * perView;
+				const uint32_t y = (uint32_t)(rem / a.W), x = (uint32_t)(rem - (unsigned long long)y * a.W);
+				const size_t p = (size_t)view * a.viewPixels + (size_t)y * a.W + x;
+				float camv[15];
+				for (int i = 0; i < 15; i++) camv[i] = __ldg(a.cams + (size_t)view * 15 + i);
+				primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
+				if (a.hits)
+				{
+					c.hitOut = a.hits + 4 * p;
+					*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+				}
+				colour = march_scene_flat<ST, ALGO, false, kPpInline>(c, o, d, a.scale, unused);
+				a.rgb[3 * p] = (uint8_t)(colour >> 16); a.rgb[3 * p + 1] = (uint8_t)((colour >> 8) & 0xFF); a.rgb[3 * p + 2] = (uint8_t)(colour & 0xFF);
+			}
+			else
+			{
+				for (int k = 0; k < 3; k++) { o[k] = __ldg(a.rays + 6 * idx + k); d[k] = __ldg(a.rays + 6 * idx + 3 + k); }
+				if (a.hits)
+				{
+					c.hitOut = a.hits + 4 * idx;
+					*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+				}
+				colour = march_scene_flat<ST, ALGO, false, kPpInline>(c, o, d, a.scale, unused);
+				a.colour[idx] = colour;
+			}
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		__threadfence();
+		const unsigned int done = atomicAdd(a.parkCtl + 1, 1u);
+		if (done == gridDim.x - 1) { a.parkCtl[0] = 0u; a.parkCtl[1] = 0u; }
+	}
+}
+
 // The storage seam on global voxel coordinates (StorageStructure.cuh:12-17).
 template <int ST>
 __global__ void lookup_kernel(SceneView sv, const int32_t* __restrict__ xyz, unsigned long long n, uint32_t* __restrict__ out, uint8_t* __restrict__ exists)
@@ -468,6 +646,7 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 	a.scale = static_cast<float>(scale);  // Ray.cuh:16
 	a.stats = s->statsEnabled ? s->d_stats : nullptr;
 	a.defer = nullptr;
+	a.parkBits = nullptr; a.parkCtl = nullptr;
 }
 
 constexpr unsigned int kDeferCapacity = 16384;  // parked rays per launch (a 4K frame of the 2048^3 orbit parks a few dozen); VRM_DEFER_CAPACITY overrides (tests)
@@ -505,12 +684,41 @@ template <int ST, int ALGO, class Args> void launch_resume(vrm_scene* s, const A
 	}
 }
 
+// Bitmap + counters of the lean kernels: sized for the launch (grow-only), all-zero between launches (resume_lean_kernel cleans up).
+int prepare_park(vrm_scene* s, unsigned long long totalRays, uint32_t** bits, unsigned int** ctl)
+{
+	const size_t words = (size_t)((totalRays + 31ull) >> 5);
+	if (!s->d_parkCtl)
+	{
+		VRM_CUDA(s, cudaMalloc(&s->d_parkCtl, 2 * sizeof(unsigned int)));
+		VRM_CUDA(s, cudaMemsetAsync(s->d_parkCtl, 0, 2 * sizeof(unsigned int), s->stream));
+	}
+	if (s->parkWords < words)
+	{
+		if (s->d_parkBits) { VRM_CUDA(s, cudaStreamSynchronize(s->stream)); cudaFree(s->d_parkBits); s->d_parkBits = nullptr; s->parkWords = 0; }
+		VRM_CUDA(s, cudaMalloc(&s->d_parkBits, words * 4));
+		VRM_CUDA(s, cudaMemsetAsync(s->d_parkBits, 0, words * 4, s->stream));
+		s->parkWords = words;
+	}
+	*bits = s->d_parkBits; *ctl = s->d_parkCtl;
+	return VRM_OK;
+}
+
 template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim3 grid)
 {
 	// Which form of the traversal runs is a measured choice per combination (512^3 terrain, 4K, B200):
 	// the per-lane state machine wins where cluster jumps nest inside the longest-axis loop (VCS + longest axis: 1.50 ms
 	// vs 2.9 ms nested); the nested loops win elsewhere (VCS + original 1.05 vs 1.16 ms, hash table 2.95 / 3.08 vs 3.45 / 3.94 ms).  VRM_RENDER_MODE=0|1|2 forces one form for A/B runs.
-	const int mode = s->renderMode >= 0 ? s->renderMode : ((ST == kStorageVcs && ALGO != kAlgoOriginal) ? 2 : 1);
+	int mode = s->renderMode >= 0 ? s->renderMode : ((ST == kStorageVcs && ALGO != kAlgoOriginal) ? 2 : 1);
+	if (mode == 3 && s->statsEnabled) mode = 2;  // the event counters live in the generic machine
+	if (mode == 3)  // lean state machine (vrm_lean.cuh) + re-trace of the rays it parked
+	{
+		const unsigned long long totalRays = (unsigned long long)a.nViews * a.W * a.H;
+		if (prepare_park(s, totalRays, &a.parkBits, &a.parkCtl) != VRM_OK) return;
+		render_lean_kernel<ST, ALGO><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		resume_lean_kernel<ST, ALGO, true, RenderArgs><<<(unsigned)s->numSms, kResumeLeanThreads, 0, s->stream>>>(a, totalRays);
+		return;
+	}
 	if (mode == 1)  // nested form, one CTA per 32x4 pixels
 	{
 		if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
@@ -545,7 +753,15 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 	// Arbitrary (incoherent) rays: the per-lane state machine measured faster than the nested loops for every combination
 	// (1024^3 sparse shells, 8.3 M random rays: original 11.7 vs 21.1 ms, longest axis 28.4 vs 31.2 ms), so it is the
 	// default here; VRM_RENDER_MODE=1 forces the nested form.
-	const int mode = s->renderMode == 1 ? 1 : 2;
+	int mode = s->renderMode == 1 ? 1 : (s->renderMode == 3 ? 3 : 2);
+	if (mode == 3 && s->statsEnabled) mode = 2;
+	if (mode == 3)
+	{
+		if (prepare_park(s, a.n, &a.parkBits, &a.parkCtl) != VRM_OK) return;
+		trace_lean_kernel<ST, ALGO><<<(unsigned)((a.n + kLeanTraceThreads - 1) / kLeanTraceThreads), kLeanTraceThreads, 0, s->stream>>>(a);
+		resume_lean_kernel<ST, ALGO, false, TraceArgs><<<(unsigned)s->numSms, kResumeLeanThreads, 0, s->stream>>>(a, a.n);
+		return;
+	}
 	if (mode == 2)
 	{
 		a.defer = prepare_defer_queue<ST, ALGO>(s);
