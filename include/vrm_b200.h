@@ -177,6 +177,38 @@ int vrm_peer_free(int device, void* d_ptr);    /* for pointers from vrm_peer_all
 /* cudaMemcpy (device to device, synchronous) between raw device pointers, e.g. out of a peer buffer into a framework tensor. */
 int vrm_copy_device(int device, void* d_dst, const void* d_src, uint64_t bytes);
 
+/* Completion flags for the one-process-per-GPU form.  After vrm_scene_set_completion_flag every render launch of the handle
+ * (vrm_render_device, vrm_render_views_device[_strided]: one launch = one sequence number) is followed, in stream order, by a
+ * store of first_value, first_value + 1, ... with release semantics at system scope into *d_flag -- a word in device memory,
+ * normally inside the gatherer's peer buffer (vrm_peer_open), so that the gatherer learns that a rank's frames have landed
+ * without a collective.  d_flag NULL switches the signal off.  vrm_wait_flags_device enqueues, on a stream of `device`, a
+ * one-warp kernel that returns when every word d_flags[i * stride_words], i < n_flags, has reached min_value (compared modulo
+ * 2^32) or timeout_ms has passed, in which case it stores 1 into *d_status (device memory, nullable).  Replaces the per-step
+ * 4-byte NCCL all-reduce of round 1; the reference has no counterpart (main/Main.cu:158: cudaDeviceSynchronize on one device). */
+int vrm_scene_set_completion_flag(vrm_scene* scene, uint32_t* d_flag, uint32_t first_value);
+/* The counting form, for views that are claimed dynamically (nobody knows in advance how many launches a rank will make): every
+ * render launch is followed by a system-scope atomic add of its number of views to *d_counter; the gatherer waits for the
+ * counter to reach the batch size with vrm_wait_flags_device(..., n_flags = 1, min_value = n_views).  NULL switches it off.
+ * vrm_claim_next enqueues on `cuda_stream` a one-thread kernel that takes the next unclaimed view index from *d_counter (a word
+ * in the gatherer's memory, system-scope atomic add of 1) and writes it to *h_claimed, page-locked host memory of the caller:
+ * synchronise the stream, read the index, render that view -- ranks that finish cheap views early simply claim more. */
+int vrm_scene_set_completion_counter(vrm_scene* scene, uint32_t* d_counter);
+int vrm_claim_next(int device, void* cuda_stream, uint32_t* d_counter, uint32_t* h_claimed);
+int vrm_wait_flags_device(int device, void* cuda_stream, const uint32_t* d_flags, uint32_t n_flags, uint32_t stride_words,
+                          uint32_t min_value, uint32_t timeout_ms, int* d_status);
+
+/* SURVEY.md 8b `render_views(handles[], cameras[], nviews, ...)`: ONE process driving several devices.  scenes[i] are built
+ * handles holding the same voxels, normally one per device (several on one device work too).  The n_views cameras are claimed
+ * dynamically -- every handle keeps two single-view launches in flight and takes the next unclaimed view when one finishes --
+ * and every frame is stored by its render kernel straight into the gather buffer on scenes[0]'s device (NVLink peer access;
+ * without it: local frame + cudaMemcpyPeerAsync).  rgb_out = n_views x H x W x 3 bytes: a device buffer on scenes[0]'s device
+ * when out_on_device != 0, else host memory (copied from the gather buffer at the end).  views_per_scene_out (nullable,
+ * n_scenes entries) reports how the views were dealt out; total_ms (nullable) is host wall time of the whole call.  Frames
+ * are identical to vrm_render of the same camera.  The call returns when every frame is complete. */
+int vrm_render_views_sharded(vrm_scene* const* scenes, uint32_t n_scenes, const float* cameras, uint32_t n_views,
+                             const float translation[3], uint32_t scale, int algorithm, uint32_t width, uint32_t height,
+                             uint8_t* rgb_out, int out_on_device, uint32_t* views_per_scene_out, float* total_ms);
+
 /* The storage seam on GLOBAL voxel coordinates: out[i] = colour or VRM_EMPTY; exists_out[i] (nullable) =
  * doesVoxelSpaceExist (always 1 inside a non-empty region for the hash table; cluster occupancy for the VCS). */
 int vrm_lookup(vrm_scene* scene, const int32_t* xyz, uint64_t n, uint32_t* out, uint8_t* exists_out);

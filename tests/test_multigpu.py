@@ -123,17 +123,42 @@ def _peer_worker(rank, world, port, q):
         s.generate_voxel_scene("vcs")          # the structure is replicated: every rank builds its own
         buf = multigpu.PeerFrameBuffer(n, w, h, 0)
         mine = multigpu.shard_views_interleaved(n, world, rank)
-        if mine:
-            # round-robin shard in ONE launch: view v of this rank goes to global slot rank + v * world
-            s.render_views_device(w, h, "longestaxis", [cams[i] for i in mine], buf.ptr_for(rank), view_stride=world)
-        s.synchronize()
-        dist.barrier()                          # (bench.py uses a 4-byte all-reduce for the same purpose)
+        # completion without a collective: the launch is followed by a release store of sequence number 1 into this rank's word of
+        # rank 0's buffer; rank 0 waits for every word on its own stream (bench.py does the same across NVLink)
+        s.set_completion_flag(buf.flag_ptr(rank), 1)
+        assert len(mine) > 0
+        # round-robin shard in ONE launch: view v of this rank goes to global slot rank + v * world
+        s.render_views_device(w, h, "longestaxis", [cams[i] for i in mine], buf.ptr_for(rank), view_stride=world)
         if rank == 0:
+            status = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+            buf.wait_flags(torch.cuda.current_stream().cuda_stream, 1, timeout_ms=60000, d_status_ptr=status.data_ptr())
+            torch.cuda.synchronize()
+            assert int(status.item()) == 0, "timed out waiting for the completion words"
             gathered = buf.to_tensor().cpu().numpy()
             local = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda:0")
             s.render_views_device(w, h, "longestaxis", cams, local.data_ptr())
             s.synchronize()
-            q.put((bool(np.array_equal(gathered, local.cpu().numpy())), int(gathered.any(axis=(1, 2, 3)).sum())))
+            first = (bool(np.array_equal(gathered, local.cpu().numpy())), int(gathered.any(axis=(1, 2, 3)).sum()))
+        s.set_completion_flag(None)
+        # ---- the same batch with DYNAMICALLY claimed views (multigpu.render_views_dynamic: claim counter + frames-landed counter in rank 0's buffer)
+        dist.barrier()
+        if rank == 0:
+            buf.reset_counters()
+        dist.barrier()
+        stream, claim_stream = torch.cuda.Stream(), torch.cuda.Stream()
+        s.set_stream(stream.cuda_stream)
+        mine_dyn = multigpu.render_views_dynamic(s, buf, list(reversed(cams)), w, h, "longestaxis", stream, claim_stream, scale=1)
+        counts = [None, None]
+        dist.all_gather_object(counts, mine_dyn)
+        if rank == 0:
+            status = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+            buf.wait_counter(stream.cuda_stream, n, timeout_ms=60000, d_status_ptr=status.data_ptr())
+            torch.cuda.synchronize()
+            assert int(status.item()) == 0, "timed out waiting for the frames-landed counter"
+            gathered = buf.to_tensor().cpu().numpy()
+            ok_dyn = bool(np.array_equal(gathered, local.flip(0).cpu().numpy())) and sum(counts) == n
+            q.put((first[0] and ok_dyn, first[1]))
+        s.reset_stream()
         dist.barrier()                          # the owner frees the buffer only after every rank is done with it
         buf.close()
         s.close()
@@ -156,3 +181,69 @@ def test_fused_peer_memory_exchange_two_processes_one_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert equal and frames == 5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("storage,algo", [("vcs", "longestaxis"), ("hashtable", "original")])
+def test_render_views_sharded_c_abi_one_process(storage, algo):
+    """vrm_render_views_sharded (SURVEY.md 8b render_views(handles[], ...)): ONE process, several handles -- here two replicas on
+    device 0, and as many more as the box has GPUs -- dynamic view claiming, frames gathered on the first handle's device.  Every
+    frame equals the single render of its camera; every view is rendered exactly once; host and device outputs agree."""
+    xyz, rgb = scenes.probe_scene()
+    w, h, n = 320, 180, 9
+    cams = [api.Camera((6.0 + 0.7 * i, 2.0 + 0.3 * i, 6.0 - 0.5 * i), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h)) for i in range(n)]
+    devices = [0, 0] + list(range(1, min(api.load_library().vrm_device_count(), 4)))
+    replicas = []
+    for d in devices:
+        s = api.VoxelScene(d)
+        s.add_voxels(xyz, rgb)
+        s.generate_voxel_scene(storage)
+        replicas.append(s)
+    want = np.stack([replicas[0].render(w, h, algo, c, scale=8)["rgb"] for c in cams])
+    got = api.render_views_sharded(replicas, w, h, algo, cams, scale=8)
+    assert np.array_equal(got["rgb"], want)
+    assert sum(got["views_per_scene"]) == n and len(got["views_per_scene"]) == len(replicas)
+    dev_out = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda:0")
+    got2 = api.render_views_sharded(replicas, w, h, algo, cams, scale=8, d_rgb_ptr=dev_out.data_ptr())
+    assert got2["rgb"] is None and np.array_equal(dev_out.cpu().numpy(), want)
+    one = api.render_views_sharded(replicas[:1], w, h, algo, cams[:2], scale=8)      # a single handle, fewer views than launch slots
+    assert np.array_equal(one["rgb"], want[:2]) and one["views_per_scene"] == [2]
+    pinned = torch.zeros((n, h, w, 3), dtype=torch.uint8).pin_memory()                # one handle + pinned frames: stored directly
+    api.render_views_sharded(replicas[:1], w, h, algo, cams, scale=8, rgb_out=pinned.numpy())
+    assert np.array_equal(pinned.numpy(), want)
+    with pytest.raises(api.VrmError):
+        api.render_views_sharded([replicas[0], replicas[0]], w, h, algo, cams, scale=8)
+    for s in replicas:
+        s.close()
+
+
+@pytest.mark.gpu
+def test_completion_flag_counts_render_launches():
+    """vrm_scene_set_completion_flag: one sequence number per render launch, published behind the frame; vrm_wait_flags_device returns
+    at once when the word is there and reports a time-out (status 1) when it is not."""
+    xyz, rgb = scenes.probe_scene()
+    s = api.VoxelScene(0)
+    s.add_voxels(xyz, rgb)
+    s.generate_voxel_scene("vcs")
+    lib = api.load_library()
+    w, h = 160, 90
+    cam = api.Camera.reference_default(w, h)
+    fb = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda:0")
+    flag = torch.zeros(64, dtype=torch.int32, device="cuda:0")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    s.set_completion_flag(flag.data_ptr(), 5)
+    for algo in ("longestaxis", "original", "longestaxis"):
+        s.render_device(w, h, algo, cam, fb.data_ptr(), scale=8)
+    import ctypes as C
+    assert lib.vrm_wait_flags_device(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(flag.data_ptr()), 1, 64, 7, 5000, C.c_void_p(status.data_ptr())) == 0
+    torch.cuda.synchronize()
+    assert int(flag[0].item()) == 7 and int(status.item()) == 0
+    assert lib.vrm_wait_flags_device(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(flag.data_ptr()), 1, 64, 8, 50, C.c_void_p(status.data_ptr())) == 0
+    torch.cuda.synchronize()
+    assert int(status.item()) == 1                      # nobody publishes 8: the wait gives up after 50 ms
+    s.set_completion_flag(None)
+    s.render_device(w, h, "longestaxis", cam, fb.data_ptr(), scale=8)
+    s.synchronize()
+    assert int(flag[0].item()) == 7
+    s.close()

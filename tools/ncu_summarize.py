@@ -92,7 +92,8 @@ def main():
         first = launches[0]
         allw[workload] = {"dram_bytes_per_launch": first["dram_bytes"], "l2_hit_pct": first.get("l2_hit_pct"), "l1_hit_pct": first.get("l1_hit_pct"),
                           "issue_slot_utilisation_pct": first.get("issue_slot_utilisation_pct"), "warp_execution_efficiency_pct": first["warp_execution_efficiency_pct"],
-                          "duration_ms_under_ncu": first.get("duration_ms"), "source": os.path.basename(out) + ".json"}
+                          "duration_ms_under_ncu": first.get("duration_ms"), "warp_instructions_per_launch": first.get("warp_instructions"),
+                          "threads_per_instruction": first.get("threads_per_instruction"), "kernel": first.get("kernel"), "source": os.path.basename(out) + ".json"}
         json.dump(allw, open(path, "w"), indent=1)
     print(json.dumps(launches[0], indent=1))
 

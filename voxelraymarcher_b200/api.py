@@ -35,6 +35,7 @@ EXPORTS = [
     "vrm_scene_build", "vrm_scene_info", "vrm_set_lighting", "vrm_camera_make", "vrm_make_unit_vector", "vrm_render",
     "vrm_render_device", "vrm_render_views_device", "vrm_render_views_device_strided", "vrm_render_views", "vrm_trace_rays", "vrm_trace_rays_device", "vrm_lookup",
     "vrm_set_l2_persistence", "vrm_set_statistics", "vrm_get_statistics", "vrm_peer_alloc", "vrm_peer_open", "vrm_peer_close", "vrm_peer_free", "vrm_copy_device", "vrm_microbench_l2",
+    "vrm_scene_set_completion_flag", "vrm_scene_set_completion_counter", "vrm_claim_next", "vrm_wait_flags_device", "vrm_render_views_sharded",
 ]
 
 
@@ -95,6 +96,11 @@ def load_library():
         "vrm_set_statistics": (ci, [vp, ci]),
         "vrm_get_statistics": (ci, [vp, vp]),
         "vrm_microbench_l2": (ci, [ci, u64, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]),
+        "vrm_scene_set_completion_flag": (ci, [vp, vp, u32]),
+        "vrm_scene_set_completion_counter": (ci, [vp, vp]),
+        "vrm_claim_next": (ci, [ci, vp, vp, vp]),
+        "vrm_wait_flags_device": (ci, [ci, vp, vp, u32, u32, u32, u32, vp]),
+        "vrm_render_views_sharded": (ci, [vp, u32, vp, u32, vp, u32, ci, u32, u32, vp, ci, vp, C.POINTER(f32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -338,6 +344,15 @@ class VoxelScene:
         self._check(self.lib.vrm_lookup(self.h, _ptr(xyz), n, _ptr(out), _ptr(exists)), "vrm_lookup")
         return out, exists
 
+    def set_completion_flag(self, d_flag_ptr: int | None, first_value: int = 1):
+        """Every later render launch of this scene stores first_value, first_value + 1, ... into the word at ``d_flag_ptr`` (device or
+        peer memory) behind its frame (``multigpu.PeerFrameBuffer.flag_ptr``); ``None`` switches the signal off."""
+        self._check(self.lib.vrm_scene_set_completion_flag(self.h, C.c_void_p(d_flag_ptr or 0), first_value), "vrm_scene_set_completion_flag")
+
+    def set_completion_counter(self, d_counter_ptr: int | None):
+        """Counting form of the completion signal: every render launch adds its number of views to the word at ``d_counter_ptr``."""
+        self._check(self.lib.vrm_scene_set_completion_counter(self.h, C.c_void_p(d_counter_ptr or 0)), "vrm_scene_set_completion_counter")
+
     # -- statistics ----------------------------------------------------------------------------------------------
     def set_l2_persistence(self, enabled: bool):
         self._check(self.lib.vrm_set_l2_persistence(self.h, int(enabled)), "vrm_set_l2_persistence")
@@ -350,3 +365,26 @@ class VoxelScene:
         self._check(self.lib.vrm_get_statistics(self.h, _ptr(out)), "vrm_get_statistics")
         keys = ["exist_checks", "exist_false", "lookups", "lookup_hits", "table2_probes", "region_reads", "rays", "crawl_skipped"]
         return {k: int(v) for k, v in zip(keys, out)}
+
+
+def render_views_sharded(scene_list, width, height, algorithm, cameras, scale=1, translation=(0.0, 0.0, 0.0), rgb_out=None, d_rgb_ptr: int | None = None):
+    """``vrm_render_views_sharded``: ONE process, one built ``VoxelScene`` per device (same voxels); the views are claimed dynamically
+    and gathered on the first scene's device.  Returns dict(rgb[n,H,W,3] | None, views_per_scene, total_ms); with ``d_rgb_ptr`` the
+    frames stay in that device buffer (on the first scene's device)."""
+    lib = load_library()
+    cams = np.ascontiguousarray(np.stack([VoxelScene._cam(c) for c in cameras]).astype(np.float32))
+    n = cams.shape[0]
+    handles = (C.c_void_p * len(scene_list))(*[s.h for s in scene_list])
+    counts = np.zeros(len(scene_list), np.uint32)
+    ms = C.c_float()
+    on_device = d_rgb_ptr is not None
+    if not on_device:
+        if rgb_out is None:
+            rgb_out = np.zeros((n, height, width, 3), np.uint8)
+        assert rgb_out.dtype == np.uint8 and rgb_out.size == n * height * width * 3 and rgb_out.flags["C_CONTIGUOUS"]
+    out = C.c_void_p(d_rgb_ptr) if on_device else _ptr(rgb_out)
+    rc = lib.vrm_render_views_sharded(C.cast(handles, C.c_void_p), len(scene_list), _ptr(cams), n, _ptr(_f3(translation)), int(scale),
+                                      VoxelScene._algo(algorithm), width, height, out, int(on_device), _ptr(counts), C.byref(ms))
+    if rc:
+        raise VrmError(f"vrm_render_views_sharded: {lib.vrm_error_string(rc).decode()}: {lib.vrm_last_error(scene_list[0].h).decode()}")
+    return dict(rgb=None if on_device else rgb_out.reshape(n, height, width, 3), views_per_scene=counts.tolist(), total_ms=ms.value)

@@ -200,7 +200,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	vrm_free_async(s, s->d_regionMinMax); s->d_regionMinMax = nullptr;
 	vrm_free_structure(s);
 	cudaStreamSynchronize(s->stream);
-	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer); cudaFree(s->d_parkBits); cudaFree(s->d_parkCtl);
+	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer); cudaFree(s->d_parkBits); cudaFree(s->d_parkCtl); cudaFree(s->d_gather);
 	if (s->h_cams) cudaFreeHost(s->h_cams);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);

@@ -75,6 +75,13 @@ struct vrm_scene
 	cudaStream_t l2WindowStream = nullptr;  // stream the window is currently installed on
 	bool l2WindowOn = false;
 
+	// multi-GPU (vrm_multi.cu): word of the gatherer's memory that receives a sequence number after every render launch, and the
+	// root handle's gather buffer of vrm_render_views_sharded
+	uint32_t* d_doneFlag = nullptr;
+	uint32_t doneSeq = 0;
+	uint32_t* d_doneCounter = nullptr;  // counting form: += frames of the launch (dynamically claimed views)
+	uint8_t* d_gather = nullptr;      size_t gatherBytes = 0;
+
 	bool statsEnabled = false;
 	vrm::Stats* d_stats = nullptr;
 	uint64_t statsRays = 0;
@@ -117,6 +124,9 @@ void vrm_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint3
 
 // vrm_api.cu: install / remove the access-policy window on the handle's current stream (called by the launch wrappers)
 void vrm_apply_l2_window(vrm_scene* s);
+
+// vrm_multi.cu: publish the handle's next completion sequence number behind the launches already on its stream (no-op without a flag)
+void vrm_signal_completion(vrm_scene* s, uint32_t frames);
 
 // vrm_render.cu
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,

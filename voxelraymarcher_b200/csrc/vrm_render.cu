@@ -809,6 +809,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	else if (orig) launch_render_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
 	else launch_render_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
 	VRM_CUDA(s, cudaGetLastError());
+	if (yEnd == H) vrm_signal_completion(s, nViews);  // (a band launch signals with the frame's last band)
 	return VRM_OK;
 }
 

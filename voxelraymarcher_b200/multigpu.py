@@ -93,9 +93,13 @@ class PeerFrameBuffer:
         self.shape = (n_frames, height, width, 3)
         self.owner = self.rank == dst
         self.ptr = C.c_void_p()
+        # behind the frames: one completion word per rank, 256 bytes apart (vrm_scene_set_completion_flag / wait_flags)
+        self.world = dist.get_world_size(group)
+        self.flags_offset = (n_frames * self.frame_bytes + 255) // 256 * 256
         handle = (C.c_ubyte * 64)()
         if self.owner:
-            rc = self.lib.vrm_peer_alloc(device, n_frames * self.frame_bytes, C.byref(self.ptr), C.cast(handle, C.c_void_p))
+            # (+ two more words behind the per-rank flags: the view-claim counter and the frames-landed counter of render_views_dynamic)
+            rc = self.lib.vrm_peer_alloc(device, self.flags_offset + 256 * (self.world + 2), C.byref(self.ptr), C.cast(handle, C.c_void_p))
             if rc:
                 raise api.VrmError(f"vrm_peer_alloc failed: {rc}")
         box = [bytes(handle) if self.owner else None]
@@ -108,6 +112,41 @@ class PeerFrameBuffer:
 
     def ptr_for(self, slot: int) -> int:
         return self.ptr.value + slot * self.frame_bytes
+
+    FLAG_STRIDE_WORDS = 64
+
+    def flag_ptr(self, rank: int) -> int:
+        """Device pointer of ``rank``'s completion word (zero after allocation)."""
+        return self.ptr.value + self.flags_offset + 256 * rank
+
+    def counter_ptr(self, which: int) -> int:
+        """0: next unclaimed view (vrm_claim_next); 1: frames landed (vrm_scene_set_completion_counter).  Zero after allocation."""
+        return self.ptr.value + self.flags_offset + 256 * (self.world + which)
+
+    def reset_counters(self):
+        """Owner only, between batches (synchronous)."""
+        import torch
+        zero = torch.zeros(128, dtype=torch.int32, device=f"cuda:{self.device}")
+        import ctypes as C
+        rc = self.lib.vrm_copy_device(self.device, C.c_void_p(self.counter_ptr(0)), C.c_void_p(zero.data_ptr()), 512)
+        if rc:
+            raise RuntimeError(f"vrm_copy_device failed: {rc}")
+
+    def wait_counter(self, cuda_stream_ptr: int, n_frames: int, timeout_ms: int = 20000, d_status_ptr: int | None = None):
+        """Owner only: enqueue a wait until ``n_frames`` frames have landed (counting completion signal)."""
+        import ctypes as C
+        rc = self.lib.vrm_wait_flags_device(self.device, C.c_void_p(cuda_stream_ptr), C.c_void_p(self.counter_ptr(1)), 1, 1, n_frames, timeout_ms,
+                                            C.c_void_p(d_status_ptr or 0))
+        if rc:
+            raise RuntimeError(f"vrm_wait_flags_device failed: {rc}")
+
+    def wait_flags(self, cuda_stream_ptr: int, min_value: int, timeout_ms: int = 20000, d_status_ptr: int | None = None):
+        """Owner only: enqueue on ``cuda_stream_ptr`` a wait until every rank's completion word has reached ``min_value``."""
+        import ctypes as C
+        rc = self.lib.vrm_wait_flags_device(self.device, C.c_void_p(cuda_stream_ptr), C.c_void_p(self.flag_ptr(0)), self.world, self.FLAG_STRIDE_WORDS,
+                                            min_value, timeout_ms, C.c_void_p(d_status_ptr or 0))
+        if rc:
+            raise RuntimeError(f"vrm_wait_flags_device failed: {rc}")
 
     def to_tensor(self):
         """Owner only: copy the gathered frames into a fresh torch tensor (after the producers have been synchronised)."""
@@ -124,3 +163,43 @@ class PeerFrameBuffer:
         if self.ptr and self.ptr.value:
             (self.lib.vrm_peer_free if self.owner else self.lib.vrm_peer_close)(self.device, self.ptr)
             self.ptr.value = None
+
+
+def render_views_dynamic(scene, peer: PeerFrameBuffer, cameras: Sequence, width: int, height: int, algorithm, stream, claim_stream, scale=1,
+                         translation=(0.0, 0.0, 0.0)) -> int:
+    """One rank's part of a view batch whose views are claimed DYNAMICALLY from a counter in the gatherer's memory (BASELINE.json
+    configs[3]: the views of an orbit differ in cost, static blocks or round-robin leave ranks idle at the end).  The rank keeps one
+    frame rendering and one claimed: the claim for the next view runs on ``claim_stream`` while the current frame renders on
+    ``stream``.  Every frame is stored by its kernel into slot ``view`` of ``peer`` and counted there (``peer.wait_counter`` on the
+    owner).  Call ``peer.reset_counters()`` on the owner and a barrier before every batch.  Returns the number of views rendered here."""
+    import ctypes as C
+
+    import torch
+
+    lib = peer.lib
+    n = len(cameras)
+    claimed = torch.zeros(2, dtype=torch.int32).pin_memory()
+    scene.set_completion_counter(peer.counter_ptr(1))
+    rendered = 0
+
+    def claim(slot):
+        rc = lib.vrm_claim_next(peer.device, C.c_void_p(claim_stream.cuda_stream), C.c_void_p(peer.counter_ptr(0)), C.c_void_p(claimed.data_ptr() + 4 * slot))
+        if rc:
+            raise RuntimeError(f"vrm_claim_next failed: {rc}")
+
+    try:
+        claim(0)
+        k = 0
+        while True:
+            claim_stream.synchronize()
+            v = int(claimed[k & 1].item())
+            if v >= n:
+                break
+            scene.render_device(width, height, algorithm, cameras[v], peer.ptr_for(v), scale=scale, translation=translation)
+            rendered += 1
+            k += 1
+            claim(k & 1)          # fetched while the frame above renders
+        stream.synchronize()
+    finally:
+        scene.set_completion_counter(None)
+    return rendered
