@@ -57,6 +57,7 @@ def _lib(kind: str):
         if kind == "refh":
             sig["scene_add_cube"] = (None, [vp, i32, i32, i32, i32])
             sig["scene_add_sphere"] = (None, [vp, u32, u32, u32, u32, C.c_int])
+            sig["scene_load_file"] = (None, [vp, C.c_char_p])
         if kind in ("refg", "refgx"):
             sig["last_kernel_ms"] = (C.c_float, [])
             sig["render_timed"] = (C.c_int, [vp, vp, vp, u32, C.c_int, u32, u32, C.c_int, C.c_int, vp])
@@ -128,6 +129,15 @@ class OracleScene:
         rgb = np.ascontiguousarray(rgb, np.uint32).reshape(-1)
         assert xyz.shape[0] == rgb.shape[0]
         self._fn("scene_add_voxels")(self.h, _ptr(xyz), _ptr(rgb), xyz.shape[0])
+
+    def load_file(self, directory: str, filename: str = "scene.vox"):
+        """VoxelFile::readVoxelFile on ``directory``/resources/``filename`` (the reference resolves the path against the working directory)."""
+        here = os.getcwd()
+        os.chdir(directory)
+        try:
+            self._fn("scene_load_file")(self.h, filename.encode())
+        finally:
+            os.chdir(here)
 
     def add_cube(self, x, y, z, hw):
         self._fn("scene_add_cube")(self.h, x, y, z, hw)

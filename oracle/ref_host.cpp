@@ -12,6 +12,7 @@
 //   rayMarchVoxelScene / rayMarchVoxelSceneLongestAxis (renderer/Renderer.cuh:338, 917)
 //   Camera::Camera                                     (renderer/camera/Camera.cuh:11-23)
 //   VoxelCube / VoxelSphere generators                 (geometry/VoxelCube.cuh, VoxelSphere.cuh)
+//   VoxelFile::readVoxelFile                           (geometry/VoxelFile.cuh:9-35; reads "resources/<name>" under the working directory)
 // plus a recording StorageStructure wrapper (the reference's own virtual seam,
 // storage/StorageStructure.cuh:12-17) that extracts the per-pixel first-hit voxel, which the
 // reference itself never outputs, and counts lookups for the roofline model.
@@ -28,6 +29,7 @@ thread_local dim3 blockDim;
 #include <mutex>
 
 #include "geometry/VoxelCube.cuh"
+#include "geometry/VoxelFile.cuh"
 #include "geometry/VoxelFunctions.cuh"
 #include "geometry/VoxelSceneCPU.cuh"
 #include "geometry/VoxelSphere.cuh"
@@ -140,6 +142,12 @@ void refh_scene_add_voxels(void* h, const int32_t* xyz, const uint32_t* rgb, uin
 	for (uint64_t i = 0; i < n; i++)
 		s->cpu.insertVoxel(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rgb[i]);
 	s->nInserted += n;
+}
+
+// The reference's scene reader (Main.cu:99): inserts the voxels of resources/<filename> (relative to the process' working directory).
+void refh_scene_load_file(void* h, const char* filename)
+{
+	VoxelFile::readVoxelFile(static_cast<RefScene*>(h)->cpu, filename);
 }
 
 // The reference's own (unused by its main) procedural generators, for generator parity tests.
