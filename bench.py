@@ -423,7 +423,7 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel (render): algorithmic bytes from the kernel's own event counters, summed over the
         # frames of the timed region (statistics build of the same kernel, outside the timed region) ---------------------------
-        scene.set_statistics(True)
+        scene.set_statistics(True, as_executed=True)      # the work the timed kernels did (dead shadow rays are not traced)
         per_view = {}
         for v in sorted(set(views[args.warmup:])):
             scene.render_device(WIDTH, HEIGHT, ALGORITHM, orbit_camera(api, v), frame.data_ptr())

@@ -132,6 +132,15 @@ def test_statistics_match_oracle_counters(probe, storage):
         want = ref.render(cam.data, 320, 180, algo, scale=8, want_counters=True)["counters"]
         assert [st["exist_checks"], st["exist_false"], st["lookups"], st["lookup_hits"]] == [int(v) for v in want[:4]]
         assert st["rays"] == 320 * 180
+        # the counters of the work as executed: the production kernels do not trace the shadow ray of a pixel that is black already
+        # (a normal facing away from the light: colour * !shadow = 0 either way) -- same frame, fewer events
+        frame = s.render(320, 180, algo, cam, scale=8)["rgb"]
+        s.set_statistics(True, as_executed=True)
+        frame2 = s.render(320, 180, algo, cam, scale=8)["rgb"]
+        st2 = s.get_statistics()
+        s.set_statistics(True)
+        assert np.array_equal(frame, frame2)
+        assert st2["rays"] == st["rays"] and st2["lookup_hits"] <= st["lookup_hits"] and 0 < st2["exist_checks"] < st["exist_checks"]
 
 
 def test_edge_cases():

@@ -11,7 +11,11 @@ import sys
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], stdout=subprocess.PIPE, text=True).stdout
+    if rep.endswith(".csv.gz"):     # the source page as saved on the GPU box by tools/gpu_capture.sh
+        import gzip
+        txt = gzip.open(rep, "rt").read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     print(rows[0])

@@ -357,8 +357,11 @@ class VoxelScene:
     def set_l2_persistence(self, enabled: bool):
         self._check(self.lib.vrm_set_l2_persistence(self.h, int(enabled)), "vrm_set_l2_persistence")
 
-    def set_statistics(self, enabled: bool):
-        self._check(self.lib.vrm_set_statistics(self.h, int(enabled)), "vrm_set_statistics")
+    def set_statistics(self, enabled: bool, as_executed: bool = False):
+        """Event counters for the next render / trace calls.  Default: comparable with the reference's (every shadow ray is traced, as
+        the reference does).  ``as_executed``: the counters of the work the production kernels do -- a shadow ray whose pixel is already
+        black (normal facing away from the light: colour * !shadow = 0 either way) is not traced."""
+        self._check(self.lib.vrm_set_statistics(self.h, (2 if as_executed else 1) if enabled else 0), "vrm_set_statistics")
 
     def get_statistics(self):
         out = np.zeros(8, np.uint64)

@@ -200,7 +200,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	vrm_free_async(s, s->d_regionMinMax); s->d_regionMinMax = nullptr;
 	vrm_free_structure(s);
 	cudaStreamSynchronize(s->stream);
-	cudaFree(s->d_fb); cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer); cudaFree(s->d_parkBits); cudaFree(s->d_parkCtl); cudaFree(s->d_gather);
+	cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer); cudaFree(s->d_parkBits); cudaFree(s->d_parkCtl); cudaFree(s->d_gather); cudaFree(s->d_shadowItems); cudaFree(s->d_shadowCtl); if (s->h_stage) cudaFreeHost(s->h_stage); for (auto& e : s->evBand) if (e) cudaEventDestroy(e);
 	if (s->h_cams) cudaFreeHost(s->h_cams);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);
@@ -376,18 +376,54 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 	uint8_t* d_rgb = static_cast<uint8_t*>(device_alias(rgb_out));
 	int32_t* d_hits = hits_out ? static_cast<int32_t*>(device_alias(hits_out)) : nullptr;
 	if (d_hits && (reinterpret_cast<uintptr_t>(d_hits) & 15u)) d_hits = nullptr;  // hit records are 16-byte stores: an unaligned page-locked buffer takes the copy path
-	const bool copyRgb = d_rgb == nullptr, copyHits = hits_out && d_hits == nullptr;
+	const bool stageRgb = d_rgb == nullptr, copyHits = hits_out && d_hits == nullptr;
 	void* p;
-	if (copyRgb) { p = s->d_fb; rc = ensure(s, &p, &s->fbBytes, px * 3); s->d_fb = static_cast<uint8_t*>(p); if (rc) return rc; d_rgb = s->d_fb; }
+	if (stageRgb)
+	{
+		// Pageable frame: the kernel stores into a page-locked staging frame owned by the handle, in horizontal BANDS, and the host
+		// copies band k into the caller's memory while band k+1 renders (a cudaMemcpy into pageable memory does the same staging
+		// inside the driver, but only after the whole frame has been rendered).
+		if (s->stageBytes < px * 3)
+		{
+			VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+			if (s->h_stage) cudaFreeHost(s->h_stage);
+			s->h_stage = nullptr; s->stageBytes = 0;
+			if (cudaHostAlloc(reinterpret_cast<void**>(&s->h_stage), px * 3, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); s->lastError = "frame staging allocation failed"; return VRM_ERR_NOMEM; }
+			s->stageBytes = px * 3;
+		}
+		d_rgb = static_cast<uint8_t*>(device_alias(s->h_stage));
+		if (!d_rgb) { s->lastError = "page-locked staging frame is not mapped"; return VRM_ERR_CUDA; }
+	}
 	if (copyHits) { p = s->d_hits; rc = ensure(s, &p, &s->hitsBytes, px * 16); s->d_hits = static_cast<int32_t*>(p); if (rc) return rc; d_hits = s->d_hits; }
 	rc = upload_cameras(s, camera, 1);
 	if (rc) return rc;
 	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
-	rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, d_rgb, d_hits);
-	if (rc) return rc;
+	constexpr int kMaxBands = 8;
+	int bands = 1;
+	if (stageRgb) { bands = (int)(px * 3 / (size_t(2) << 20)); if (bands < 1) bands = 1; if (bands > kMaxBands) bands = kMaxBands; }  // >= 2 MB per band
+	uint32_t bandEnd[kMaxBands];
+	for (int b = 0; b < bands; b++) bandEnd[b] = b == bands - 1 ? height : (uint32_t)(((uint64_t)height * (b + 1) / bands + 7) & ~7ull);
+	if (stageRgb) for (int b = 0; b < bands; b++) if (!s->evBand[b]) VRM_CUDA(s, cudaEventCreateWithFlags(&s->evBand[b], cudaEventDisableTiming));
+	for (int b = 0; b < bands; b++)
+	{
+		const uint32_t y0 = b ? bandEnd[b - 1] : 0u, y1 = bandEnd[b] < height ? bandEnd[b] : height;
+		if (y1 <= y0) continue;
+		rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, d_rgb, d_hits, y0, y1);
+		if (rc) return rc;
+		if (stageRgb) VRM_CUDA(s, cudaEventRecord(s->evBand[b], s->stream));
+	}
 	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
-	if (copyRgb) VRM_CUDA(s, cudaMemcpyAsync(rgb_out, s->d_fb, px * 3, cudaMemcpyDeviceToHost, s->stream));
 	if (copyHits) VRM_CUDA(s, cudaMemcpyAsync(hits_out, s->d_hits, px * 16, cudaMemcpyDeviceToHost, s->stream));
+	if (stageRgb)
+	{
+		for (int b = 0; b < bands; b++)
+		{
+			const uint32_t y0 = b ? bandEnd[b - 1] : 0u, y1 = bandEnd[b] < height ? bandEnd[b] : height;
+			if (y1 <= y0) continue;
+			VRM_CUDA(s, cudaEventSynchronize(s->evBand[b]));
+			memcpy(rgb_out + (size_t)y0 * width * 3, s->h_stage + (size_t)y0 * width * 3, (size_t)(y1 - y0) * width * 3);
+		}
+	}
 	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
 	if (kernel_ms) VRM_CUDA(s, cudaEventElapsedTime(kernel_ms, s->ev0, s->ev1));
 	return VRM_OK;
@@ -597,6 +633,7 @@ int vrm_set_statistics(vrm_scene* s, int enabled)
 {
 	if (!s) return VRM_ERR_INVALID;
 	s->statsEnabled = enabled != 0;
+	s->statsMode = enabled == 2 ? 2 : (enabled ? 1 : 0);
 	return VRM_OK;
 }
 

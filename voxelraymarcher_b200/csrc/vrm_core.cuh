@@ -297,9 +297,6 @@ VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mul
 #ifndef VRM_COORD64_EMPTY
 #define VRM_COORD64_EMPTY 1
 #endif
-#ifndef VRM_NESTED_TWO_PHASE
-#define VRM_NESTED_TWO_PHASE 1  // nested traversal (march_scene): primary rays of a warp first, then its shadow rays together
-#endif
 #ifndef VRM_HASH_CLUSTER_FILTER
 #define VRM_HASH_CLUSTER_FILTER 1
 #endif
@@ -1024,10 +1021,22 @@ VRM_HD bool in_shadow(RayCtx<ST, STATS>& c, const float* originW, const int* reg
 
 // ---------------------------------------------------------------- scene walk
 
-// rayMarchVoxelScene (Renderer.cuh:338-434) / rayMarchVoxelSceneLongestAxis (Renderer.cuh:917-1010).
-// originW/dirW: WORLD ray (before the scene transform).  Returns the pixel colour (0 = background).
+// What a pixel's shadow phase starts from: the hit position and its region in WORLD axes, the shaded colour that survives when the
+// light is visible, and which of the reference's two shadow routines the hit site calls.  Also the record of the shadow-ray queue
+// between the primary and the shadow kernel (vrm_render.cu).
+struct ShadowStart
+{
+	float hitW[3];
+	int regW[3];
+	uint32_t lit;   // applyLighting(...) of the hit
+	int la;         // 1: isInShadowRayMarchVoxelSceneLongestAxis, 0: isInShadowOriginalRayMarch
+};
+
+// rayMarchVoxelScene (Renderer.cuh:338-434) / rayMarchVoxelSceneLongestAxis (Renderer.cuh:917-1010) up to and including the hit's
+// lighting; the shadow ray (`* !isInShadow...`, Renderer.cuh:314-315,821-822,...) is the caller's second phase (shadow_nested).
+// originW/dirW: WORLD ray (before the scene transform).  Returns true on a hit (ss filled in), false for background.
 template <int ST, int ALGO, bool STATS>
-VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
+VRM_HD bool march_scene_primary(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale, ShadowStart& ss)
 {
 	using P = typename std::conditional<ALGO == kAlgoOriginal, PermIdentity, PermRuntime>::type;
 	P p;
@@ -1052,7 +1061,7 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 		if (t1 <= 0.0f) t1 = INFINITY;
 		if (t2 <= 0.0f) t2 = INFINITY;
 		float tMin = min3(t0, t1, t2);
-		if (tMin == INFINITY) return 0;
+		if (tMin == INFINITY) return false;
 		float s = vadd(tMin, kEps);
 		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
 		reg[0] = (int)floorf(vmul(o[0], 0.015625f)); reg[1] = (int)floorf(vmul(o[1], 0.015625f)); reg[2] = (int)floorf(vmul(o[2], 0.015625f));
@@ -1063,11 +1072,9 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 	RayDir ko = k;
 	if constexpr (ALGO != kAlgoOriginal) ko = scaled_raydir(k);
 	int32_t ri = region_entry(c, p, reg);
-#if VRM_NESTED_TWO_PHASE
-	// Two phases: every lane first marches its PRIMARY ray to a hit or out of the scene -- the loop below has one exit, so the warp
-	// reconverges behind it -- and only then do the lanes that hit shade and walk their shadow rays, together.  Executed as the
-	// reference nests it (shadow march inside the hit branch inside the region loop) the shadow rays of a warp ran one hit time after
-	// the other: 11.9 of 32 threads active in the shadow half of the hash table kernels (profiles/r01j).  Same operations per ray.
+	// Every lane marches its PRIMARY ray to a hit or out of the scene -- the loop has one exit, so the warp reconverges behind it.
+	// Executed as the reference nests it (shadow march inside the hit branch inside the region loop) the shadow rays of a warp ran one
+	// hit time after the other: 11.9 of 32 threads active in the shadow half of the hash table kernels (profiles/r01j).
 	uint32_t col = kEmpty;
 	HitInfo h;
 	while (ri != -2)
@@ -1081,47 +1088,29 @@ VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const fl
 		rebase_region(o, reg);
 		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
 	}
-	uint32_t lit = 0;
-	if (col != kEmpty)
-	{
-		// applyLighting(...) * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion)  (Renderer.cuh:314-315,821-822,...)
-		float hitW[3];
-		int regW[3];
-		to_world(p, h.pos, hitW); to_world(p, reg, regW);
-		lit = apply_lighting(c.light, c.translation, col, h.nAxisW, h.nSign, hitW, regW);
-		bool shadowed;
-		if constexpr (ALGO == kAlgoOriginal) shadowed = in_shadow<ST, STATS, false>(c, hitW, regW);
-		else shadowed = h.laShadow ? in_shadow<ST, STATS, true>(c, hitW, regW) : in_shadow<ST, STATS, false>(c, hitW, regW);
-		lit *= (uint32_t)!shadowed;
-	}
-	return lit;
-#else
-	while (ri != -2)
-	{
-		ri = skip_null_regions<ST, STATS, P, false>(c, p, o, k, reg, ri);
-		if (ri == -2) return 0;
-		RegionRef<ST> r = load_region<ST>(c.sv, ri);
-		HitInfo h;
-		uint32_t col;
-		if constexpr (ALGO == kAlgoOriginal) col = march_original<ST, STATS, P>(c, r, p, o, k, reg, h);
-		else col = march_longest_axis<ST, STATS, false>(c, r, p, o, k, ko, reg, h);
-		if (col != kEmpty)
-		{
-			// applyLighting(...) * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion)  (Renderer.cuh:314-315,821-822,...)
-			float hitW[3];
-			int regW[3];
-			to_world(p, h.pos, hitW); to_world(p, reg, regW);
-			uint32_t lit = apply_lighting(c.light, c.translation, col, h.nAxisW, h.nSign, hitW, regW);
-			bool shadowed;
-			if constexpr (ALGO == kAlgoOriginal) shadowed = in_shadow<ST, STATS, false>(c, hitW, regW);
-			else shadowed = h.laShadow ? in_shadow<ST, STATS, true>(c, hitW, regW) : in_shadow<ST, STATS, false>(c, hitW, regW);
-			return lit * (uint32_t)!shadowed;
-		}
-		rebase_region(o, reg);
-		ri = position_sane(o) ? region_entry(c, p, reg) : -2;
-	}
-	return 0;
-#endif
+	if (col == kEmpty) return false;
+	// applyLighting(...)  (Renderer.cuh:314-315,821-822,...)
+	to_world(p, h.pos, ss.hitW); to_world(p, reg, ss.regW);
+	ss.lit = apply_lighting(c.light, c.translation, col, h.nAxisW, h.nSign, ss.hitW, ss.regW);
+	ss.la = ALGO == kAlgoOriginal ? 0 : h.laShadow;
+	return true;
+}
+
+// ... * !isInShadow...(Ray(hit, LIGHT_DIRECTION), currentRegion): which routine depends on the hit site
+template <int ST, int ALGO, bool STATS>
+VRM_HD bool shadow_nested(RayCtx<ST, STATS>& c, const ShadowStart& ss)
+{
+	if constexpr (ALGO == kAlgoOriginal) return in_shadow<ST, STATS, false>(c, ss.hitW, ss.regW);
+	else return ss.la ? in_shadow<ST, STATS, true>(c, ss.hitW, ss.regW) : in_shadow<ST, STATS, false>(c, ss.hitW, ss.regW);
+}
+
+// Both phases for one ray (trace kernels, host sim).  Returns the pixel colour (0 = background).
+template <int ST, int ALGO, bool STATS>
+VRM_HD uint32_t march_scene(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
+{
+	ShadowStart ss;
+	if (!march_scene_primary<ST, ALGO, STATS>(c, originW, dirW, scale, ss)) return 0;
+	return ss.lit * (uint32_t)!shadow_nested<ST, ALGO, STATS>(c, ss);
 }
 
 // calculateWorldRay (Renderer.cuh:1013-1022) + Camera::generateRay (Camera.cuh:25-29).  cam = 15 floats.

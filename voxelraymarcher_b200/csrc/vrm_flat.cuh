@@ -79,6 +79,12 @@ constexpr int32_t kRiPending = -3;       // FlatRay::ri: the ray has left its re
 //              the hot kernels: compiled into them -- even as a never-taken branch -- it cost 30 % of their speed.
 //   kPpInline  fast-forward in place (resume kernel, host harness)
 constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
+#ifndef VRM_REGION_VOTE
+#define VRM_REGION_VOTE 0  // > 0: march_scene_flat_warp runs the region-entry block only when at least this many lanes want it (or nothing else can run)
+#endif
+#ifndef VRM_HEAD_VOTE
+#define VRM_HEAD_VOTE 0    // the same for the longest-axis loop head
+#endif
 #ifndef VRM_PP_DEFAULT
 #define VRM_PP_DEFAULT 2
 #endif
@@ -292,30 +298,36 @@ struct FlatRay
 		st = kStHit;
 	}
 
-	VRM_HD void do_hit(RayCtx<ST, STATS>& c)
+	// the pending hit's lighting: where its shadow ray starts (WORLD axes) and the colour that survives when the light is visible
+	VRM_HD void shade_hit(RayCtx<ST, STATS>& c, ShadowStart& ss) const
 	{
 		const int nAxisW = mode & 3;
 		const float nSign = (mode & 4) ? -1.0f : 1.0f;
-		const bool laKind = kLA && (mode & 8) != 0;
-		float hitW[3];
-		int regW[3];
-		{
-			const PermRuntime p = unpack_perm(fl);
-			const int minC = c.sv.minCoord;
-			const int reg[3] = {(int)ur[0] + minC, (int)ur[1] + minC, (int)ur[2] + minC};
-			to_world(p, ro, hitW); to_world(p, reg, regW);
-		}
-		result = apply_lighting_flat(c.light, c.translation, result, nAxisW, nSign, hitW, regW);
-		if (!c.light.useShadows) { finish(result); return; }
+		const PermRuntime p = unpack_perm(fl);
+		const int minC = c.sv.minCoord;
+		const int reg[3] = {(int)ur[0] + minC, (int)ur[1] + minC, (int)ur[2] + minC};
+		to_world(p, ro, ss.hitW); to_world(p, reg, ss.regW);
+		ss.lit = apply_lighting_flat(c.light, c.translation, result, nAxisW, nSign, ss.hitW, ss.regW);
+		ss.la = (kLA && (mode & 8) != 0) ? 1 : 0;
+	}
+
+	// isInShadowOriginalRayMarch / isInShadowRayMarchVoxelSceneLongestAxis up to their first region (Renderer.cuh:174-199, 633-657): the
+	// ray becomes the shadow ray of `ss`; it ends with result = ss.lit (light visible) or 0 (any voxel on the way)
+	VRM_HD void start_shadow(RayCtx<ST, STATS>& c, const ShadowStart& ss)
+	{
+		const bool laKind = kLA && ss.la != 0;
+		result = ss.lit;
 		fl = kFlShadow | (laKind ? kFlShadowLA : 0u);
+		mode = kAdvNext; seq = 0; ad1 = ad2 = 0; ri = -2;
+		g[0] = g[1] = g[2] = 0; ro[0] = ro[1] = ro[2] = 0.0f;  // (every one of these is rewritten before it is read; a fresh ray of the shadow kernel starts defined)
 		PermRuntime p;
 		p.a0 = 0; p.a1 = 1; p.a2 = 2;
 		if (laKind) p = unpack_perm(c.lw.laPerm);
 		set_perm(c.sv, p);
-		to_walk(p, hitW, o);
+		to_walk(p, ss.hitW, o);
 		{
 			int regWalk[3];
-			to_walk(p, regW, regWalk);
+			to_walk(p, ss.regW, regWalk);
 			const int minC = c.sv.minCoord;
 			for (int i = 0; i < 3; i++) ur[i] = (uint32_t)(regWalk[i] - minC);
 		}
@@ -332,6 +344,14 @@ struct FlatRay
 		}
 		st = kStRegion;
 		read_region_entry(c);
+	}
+
+	VRM_HD void do_hit(RayCtx<ST, STATS>& c)
+	{
+		ShadowStart ss;
+		shade_hit(c, ss);
+		if (!c.light.useShadows) { finish(ss.lit); return; }
+		start_shadow(c, ss);
 	}
 
 	// ---- kStRegion ---------------------------------------------------------------------------------------------
@@ -783,6 +803,29 @@ struct FlatRay
 	}
 };
 
+// One pass of the marching blocks for a whole warp (all 32 lanes call it; lanes that are not marching idle).
+// VRM_REGION_VOTE / VRM_HEAD_VOTE > 0 (A/B variants): the region-entry / loop-head block of a pass runs only when enough lanes want it
+// or nobody has anything else to do; the lanes that wait keep their state and run with the lanes that join them in a later pass.
+// Progress: the main block always runs when a lane wants it; without such a lane the head block does; else the region block.
+template <int ST, int ALGO, bool STATS, int PP>
+VRM_HD void warp_march_pass(RayCtx<ST, STATS>& c, FlatRay<ST, ALGO, STATS>& ray)
+{
+#if defined(__CUDA_ARCH__) && (VRM_REGION_VOTE > 0 || VRM_HEAD_VOTE > 0)
+	const unsigned wantRegion = __ballot_sync(0xFFFFFFFFu, ray.st == kStRegion);
+	const unsigned others = __ballot_sync(0xFFFFFFFFu, ray.st == kStHead || ray.st == kStMain);
+	if (wantRegion != 0u && (VRM_REGION_VOTE <= 0 || __popc(wantRegion) >= VRM_REGION_VOTE || others == 0u)) { if (ray.st == kStRegion) ray.do_region(c); }
+	if constexpr (ALGO != kAlgoOriginal)
+	{
+		const unsigned wantHead = __ballot_sync(0xFFFFFFFFu, ray.st == kStHead);
+		const unsigned wantMain = __ballot_sync(0xFFFFFFFFu, ray.st == kStMain);
+		if (wantHead != 0u && (VRM_HEAD_VOTE <= 0 || __popc(wantHead) >= VRM_HEAD_VOTE || wantMain == 0u)) { if (ray.st == kStHead) ray.do_head(); }
+	}
+	if (ray.st == kStMain) ray.template do_main<false, PP>(c);
+#else
+	if (ray.st <= kStHead) ray.template step_marching<PP>(c);
+#endif
+}
+
 // Warp-cooperative form for the render kernels: all 32 lanes of a warp call it together (lanes without a pixel pass
 // active = false) and one ballot per iteration decides what the warp runs.
 // HIT BARRIER: lanes whose primary ray has hit wait in kStHit until every lane of the warp has hit or finished; the whole
@@ -803,7 +846,7 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 		const unsigned marching = __ballot_sync(0xFFFFFFFFu, ray.st <= kStHead);  // kStMain, kStRegion, kStHead
 		if (marching != 0u)
 		{
-			if (ray.st <= kStHead) ray.template step_marching<PP>(c);
+			warp_march_pass<ST, ALGO, STATS, PP>(c, ray);
 			continue;
 		}
 		// nobody is marching: every lane is waiting with a hit, done or parked
@@ -824,6 +867,34 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 		}
 	}
 	return ray.result;
+}
+
+// PRIMARY phase only, warp-cooperative (render kernels with the shadow-ray queue, vrm_render.cu): every lane marches its primary ray
+// until it has hit (kStHit, waiting to be shaded by the caller), finished (kStDone) or must be parked (kStPark).  No hit barrier is
+// needed: the shadow rays run in their own kernel, compacted.
+template <int ST, int ALGO, bool STATS, int PP>
+VRM_HD void march_primary_flat_warp(RayCtx<ST, STATS>& c, bool active, const float* originW, const float* dirW, float scale, FlatRay<ST, ALGO, STATS>& ray)
+{
+	ray.st = kStDone; ray.result = 0;
+	if (active) ray.start_primary(c, originW, dirW, scale);
+#if defined(__CUDA_ARCH__)
+	while (__any_sync(0xFFFFFFFFu, ray.st <= kStHead)) warp_march_pass<ST, ALGO, STATS, PP>(c, ray);
+#else
+	while (ray.st <= kStHead) ray.template step_marching<PP>(c);
+#endif
+}
+
+// SHADOW phase of one queue record, warp-cooperative: returns the pixel's final colour (ss.lit or 0); the ray may end in kStPark.
+template <int ST, int ALGO, bool STATS, int PP>
+VRM_HD void march_shadow_flat_warp(RayCtx<ST, STATS>& c, bool active, const ShadowStart& ss, FlatRay<ST, ALGO, STATS>& ray)
+{
+	ray.st = kStDone; ray.result = 0;
+	if (active) ray.start_shadow(c, ss);
+#if defined(__CUDA_ARCH__)
+	while (__any_sync(0xFFFFFFFFu, ray.st <= kStHead)) warp_march_pass<ST, ALGO, STATS, PP>(c, ray);
+#else
+	while (ray.st <= kStHead) ray.template step_marching<PP>(c);
+#endif
 }
 
 // Convenience for single-ray callers (trace kernels, host sim): run the state machine to completion.

@@ -48,12 +48,14 @@ struct vrm_scene
 	vrm::Lighting light;
 
 	// scratch owned by the handle for the host-buffer entry points
-	uint8_t* d_fb = nullptr;     size_t fbBytes = 0;
 	int32_t* d_hits = nullptr;   size_t hitsBytes = 0;
 	float* d_cams = nullptr;     size_t camsBytes = 0;
 	float* h_cams = nullptr;     // pinned staging for cameras
 	void* d_io = nullptr;        size_t ioBytes = 0;   // rays / lookup queries and results
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// vrm_render into pageable memory: page-locked staging frame written by the kernel in bands, copied out band by band
+	uint8_t* h_stage = nullptr;  size_t stageBytes = 0;
+	cudaEvent_t evBand[8] = {};
 	// streaming multi-view renders into pageable host memory (vrm_render_views): double-buffered device batches
 	cudaStream_t copyStream = nullptr;
 	cudaEvent_t evRendered[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
@@ -82,6 +84,11 @@ struct vrm_scene
 	uint32_t* d_doneCounter = nullptr;  // counting form: += frames of the launch (dynamically claimed views)
 	uint8_t* d_gather = nullptr;      size_t gatherBytes = 0;
 
+	// shadow-ray queue between the render kernels (primary rays) and shadow_kernel (vrm_render.cu): 32-byte records + {queued, claimed}
+	void* d_shadowItems = nullptr;    size_t shadowCap = 0;
+	unsigned int* d_shadowCtl = nullptr;
+
+	int statsMode = 0;                // 0 off, 1 event counters comparable with the reference (every shadow ray traced), 2 counters of the work as executed
 	bool statsEnabled = false;
 	vrm::Stats* d_stats = nullptr;
 	uint64_t statsRays = 0;

@@ -68,7 +68,54 @@ struct RenderArgs
 	uint32_t tilesX, tilesPerView, nViews;
 	uint32_t* parkBits;    // lean kernels: one bit per ray (index (view * H + y) * W + x) that must be re-traced by resume_lean_kernel
 	unsigned int* parkCtl; // {parked rays, resume blocks done}
+	int4* shadowItems;     // shadow-ray queue (two int4 per record), null when shadows are off
+	unsigned int* shadowCtl;  // {records queued, next record to claim}
+	uint32_t shadowCap;
 };
+
+// ---- shadow-ray queue ------------------------------------------------------------------------------------------------------------
+// The render kernels trace PRIMARY rays only.  A pixel whose ray hit is shaded there and its shadow ray -- start position and region in
+// world axes, the shaded colour, which of the reference's two shadow routines the hit site calls -- is appended to a queue in device
+// memory (one ballot + one atomicAdd per warp); shadow_kernel then walks the queued rays 32 consecutive records per warp.  Why: only
+// ~30 % of the pixels of the terrain frame hit anything and lit pixels' shadow rays are long while shadowed ones end early, so inside
+// the tile that found the hits the shadow phase ran at 11.8 of 32 lanes (hash table kernels, profiles/r02c) -- half of the frame time.
+// All shadow rays share one direction, so consecutive records (neighbouring pixels of a tile, tiles of a CTA) stay coherent.  Same
+// operations per ray as before; the frame receives the shaded colour first and shadow_kernel blacks out the pixels whose light is
+// blocked (Renderer.cuh:314-315: colour * !isInShadow).
+struct ShadowArgs
+{
+	SceneView sv;
+	Lighting light;
+	LightWalk lw;
+	float translation[3];
+	const int4* items;
+	unsigned int* ctl;
+	uint32_t cap;
+	uint32_t skipDead;     // 1: a record whose shaded colour is already black is not traced (0 * !shadow = 0); 0: trace everything (reference-comparable event counters)
+	uint8_t* rgb;
+	Stats* stats;
+	void* defer;
+};
+
+__device__ __forceinline__ void shadow_enqueue(const RenderArgs& a, bool want, const ShadowStart& ss, uint32_t pixel)
+{
+	const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+	if (m == 0u) return;
+	const unsigned lane = threadIdx.x & 31u;
+	const int leader = __ffs(m) - 1;
+	unsigned base = 0;
+	if ((int)lane == leader) base = atomicAdd(a.shadowCtl, (unsigned)__popc(m));
+	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	if (want)
+	{
+		const unsigned i = base + __popc(m & ((1u << lane) - 1u));
+		if (i < a.shadowCap)  // (the launch wrapper sizes the queue for every pixel of the launch)
+		{
+			a.shadowItems[2 * (size_t)i] = make_int4(__float_as_int(ss.hitW[0]), __float_as_int(ss.hitW[1]), __float_as_int(ss.hitW[2]), ss.regW[0]);
+			a.shadowItems[2 * (size_t)i + 1] = make_int4(ss.regW[1], ss.regW[2], (int)pixel, (int)(ss.lit | (ss.la ? 0x80000000u : 0u)));
+		}
+	}
+}
 
 template <bool STATS, int ST>
 __device__ __forceinline__ void flush_stats(const RayCtx<ST, STATS>& c, Stats* out)
@@ -165,9 +212,13 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
 	uint32_t color = 0;
-	if constexpr (FLATLOOP && VRM_HIT_BARRIER != 0 && ST == kStorageVcs && ALGO != kAlgoOriginal)
+	bool hit = false;
+	ShadowStart ss;
+	ss.hitW[0] = ss.hitW[1] = ss.hitW[2] = 0.0f; ss.regW[0] = ss.regW[1] = ss.regW[2] = 0; ss.lit = 0u; ss.la = 0;
+	const size_t pixel = (size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x;
+	if constexpr (FLATLOOP)
 	{
-		// warp-cooperative state machine: every lane takes part in the votes, lanes outside the image just idle
+		// warp-cooperative state machine (vrm_flat.cuh): every lane takes part in the votes, lanes outside the image just idle
 		float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
 		if (inside)
 		{
@@ -178,14 +229,28 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 			primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
 			if (a.hits)
 			{
-				c.hitOut = a.hits + 4 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x);
+				// the hit map slot is cleared here and filled at the hit site (record_hit_voxel)
+				c.hitOut = a.hits + 4 * pixel;
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
 		}
 		c.deferQueue = a.defer;
-		int slot;
-		color = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, slot);
-		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x), 0u);
+		FlatRay<ST, ALGO, STATS> ray;
+		march_primary_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, ray);
+		if (ray.st == kStHit)
+		{
+			ray.shade_hit(c, ss);
+			hit = true;
+			color = ss.lit;
+		}
+		else if (ray.st == kStPark)
+		{
+			// region-face ping-pong (vrm_flat.cuh): the ray goes to the resume kernel, which finishes it -- shadow ray included
+			const int slot = ray.park(c);
+			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * pixel, 0u);
+			else { while (ray.st < kStDone) ray.template step<kPpOff>(c); color = ray.result; }  // queue full: crawl on like the reference
+		}
+		else color = ray.result;
 	}
 	else if (inside)
 	{
@@ -194,29 +259,13 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 #pragma unroll
 		for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
 		float o[3], d[3];
-		if constexpr (FLATLOOP) primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
-		else primary_ray(camv, x, y, a.W, a.H, o, d);
-		// FLATLOOP: the same tile mapping, but each lane runs the state machine of vrm_flat.cuh (one voxel test per iteration
-		// of a single loop) instead of the nested loops of vrm_core.cuh
-		if constexpr (FLATLOOP)
-		{
-			if (a.hits)
-			{
-				// the hit map slot is cleared here and filled at the hit site (record_hit_voxel)
-				c.hitOut = a.hits + 4 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x);
-				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
-			}
-			c.deferQueue = a.defer;
-			int slot;
-			color = march_scene_flat<ST, ALGO, STATS, kPpDefer>(c, o, d, a.scale, slot);
-			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * ((size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x), 0u);
-		}
-		else
-		{
-			color = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
-			if (a.hits) reinterpret_cast<int4*>(a.hits)[(size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
-		}
+		primary_ray(camv, x, y, a.W, a.H, o, d);
+		hit = march_scene_primary<ST, ALGO, STATS>(c, o, d, a.scale, ss);
+		color = hit ? ss.lit : 0u;
+		if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 	}
+	// the shadow ray of a hit goes to the queue; without shadows (USE_SHADOWS false, Main.cu:41) the shaded colour is final
+	if (a.shadowItems) shadow_enqueue(a, hit, ss, (uint32_t)pixel);
 	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
 #if VRM_WARP_STORE
 	// per-warp staging: each warp writes its own 8x4 tile as four 24-byte row segments, no CTA barrier
@@ -256,6 +305,76 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		a.rgb[3 * p] = (uint8_t)(color >> 16);
 		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
 		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
+	}
+	flush_stats<STATS>(c, a.stats);
+}
+
+// The queued shadow rays: a persistent grid, every warp claims 32 consecutive records at a time.
+#ifndef VRM_SHADOW_MINBLOCKS
+#define VRM_SHADOW_MINBLOCKS 4
+#endif
+constexpr int kShadowThreads = 128;
+template <int ST, int ALGO, bool STATS, bool FLAT>
+__global__ void __launch_bounds__(kShadowThreads, (FLAT ? VRM_SHADOW_MINBLOCKS : (ALGO == kAlgoOriginal ? 6 : 5)) * 256 / kShadowThreads) shadow_kernel(const ShadowArgs a)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned queued = a.ctl[0];
+	const unsigned count = queued < a.cap ? queued : a.cap;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	c.deferQueue = a.defer;
+	for (;;)
+	{
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(a.ctl + 1, 32u);
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (base >= count) break;
+		const unsigned i = base + lane;
+		bool active = i < count;
+		ShadowStart ss;
+		ss.hitW[0] = ss.hitW[1] = ss.hitW[2] = 0.0f; ss.regW[0] = ss.regW[1] = ss.regW[2] = 0; ss.lit = 0u; ss.la = 0;
+		uint32_t pixel = 0;
+		if (active)
+		{
+			const int4 v0 = __ldg(a.items + 2 * (size_t)i), v1 = __ldg(a.items + 2 * (size_t)i + 1);
+			ss.hitW[0] = __int_as_float(v0.x); ss.hitW[1] = __int_as_float(v0.y); ss.hitW[2] = __int_as_float(v0.z);
+			ss.regW[0] = v0.w; ss.regW[1] = v1.x; ss.regW[2] = v1.y;
+			pixel = (uint32_t)v1.z;
+			ss.lit = (uint32_t)v1.w & 0x7FFFFFFFu;
+			ss.la = ((uint32_t)v1.w >> 31) ? 1 : 0;
+			if (a.skipDead && ss.lit == 0u) active = false;  // colour * !shadow with colour == 0
+		}
+		uint32_t final = ss.lit;
+		if constexpr (FLAT)
+		{
+			FlatRay<ST, ALGO, STATS> ray;
+			march_shadow_flat_warp<ST, ALGO, STATS, kPpDefer>(c, active, ss, ray);
+			if (active)
+			{
+				if (ray.st == kStPark)
+				{
+					const int slot = ray.park(c);
+					if (slot >= 0) { park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (size_t)pixel, 0u); final = ss.lit; }  // the resume kernel writes the pixel
+					else { while (ray.st < kStDone) ray.template step<kPpOff>(c); final = ray.result; }
+				}
+				else final = ray.result;
+			}
+		}
+		else
+		{
+			if (active && shadow_nested<ST, ALGO, STATS>(c, ss)) final = 0u;
+		}
+		if (active && final != ss.lit)
+		{
+			// the light is blocked: the shaded colour the render kernel stored becomes black
+			uint8_t* px = a.rgb + 3 * (size_t)pixel;
+			px[0] = (uint8_t)(final >> 16); px[1] = (uint8_t)((final >> 8) & 0xFF); px[2] = (uint8_t)(final & 0xFF);
+		}
 	}
 	flush_stats<STATS>(c, a.stats);
 }
@@ -649,6 +768,45 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 	a.parkBits = nullptr; a.parkCtl = nullptr;
 }
 
+// Shadow-ray queue of the handle: room for `records` records (grow-only), counters zeroed on the stream.
+int prepare_shadow_queue(vrm_scene* s, size_t records, RenderArgs& a)
+{
+	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0;
+	if (!s->light.useShadows) return VRM_OK;
+	if (!s->d_shadowCtl) VRM_CUDA(s, cudaMalloc(&s->d_shadowCtl, 2 * sizeof(unsigned int)));
+	if (s->shadowCap < records)
+	{
+		if (s->d_shadowItems) { VRM_CUDA(s, cudaStreamSynchronize(s->stream)); cudaFree(s->d_shadowItems); s->d_shadowItems = nullptr; s->shadowCap = 0; }
+		VRM_CUDA(s, cudaMalloc(&s->d_shadowItems, records * 32));
+		s->shadowCap = records;
+	}
+	VRM_CUDA(s, cudaMemsetAsync(s->d_shadowCtl, 0, 2 * sizeof(unsigned int), s->stream));
+	a.shadowItems = static_cast<int4*>(s->d_shadowItems); a.shadowCtl = s->d_shadowCtl; a.shadowCap = (uint32_t)records;
+	return VRM_OK;
+}
+
+template <int ST, int ALGO, bool FLAT> void launch_shadow(vrm_scene* s, const RenderArgs& a)
+{
+	if (!a.shadowItems) return;
+	ShadowArgs b;
+	b.sv = a.sv; b.light = a.light; b.lw = a.lw;
+	b.translation[0] = a.translation[0]; b.translation[1] = a.translation[1]; b.translation[2] = a.translation[2];
+	b.items = a.shadowItems; b.ctl = a.shadowCtl; b.cap = a.shadowCap;
+	b.skipDead = s->statsMode == 1 ? 0u : 1u;
+	b.rgb = a.rgb; b.stats = a.stats; b.defer = a.defer;
+	static int blocksPerSm[2] = {0, 0};  // per instantiation (function template static)
+	int& bps = blocksPerSm[s->statsEnabled ? 1 : 0];
+	if (bps == 0)
+	{
+		if (s->statsEnabled) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, true, FLAT>, kShadowThreads, 0);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, false, FLAT>, kShadowThreads, 0);
+		if (bps < 1) bps = 1;
+	}
+	const unsigned blocks = (unsigned)(s->numSms * bps);   // one resident wave: a multiple of the SM count
+	if (s->statsEnabled) shadow_kernel<ST, ALGO, true, FLAT><<<blocks, kShadowThreads, 0, s->stream>>>(b);
+	else shadow_kernel<ST, ALGO, false, FLAT><<<blocks, kShadowThreads, 0, s->stream>>>(b);
+}
+
 constexpr unsigned int kDeferCapacity = 16384;  // parked rays per launch (a 4K frame of the 2048^3 orbit parks a few dozen); VRM_DEFER_CAPACITY overrides (tests)
 
 // The queue exists only for VCS + longest axis (the one combination that can ping-pong): reset its counter before the launch.
@@ -719,18 +877,25 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 		resume_lean_kernel<ST, ALGO, true, RenderArgs><<<(unsigned)s->numSms, kResumeLeanThreads, 0, s->stream>>>(a, totalRays);
 		return;
 	}
-	if (mode == 1)  // nested form, one CTA per 32x4 pixels
+	if (mode == 1 || mode == 2)
 	{
-		if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
-		else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
-		return;
-	}
-	if (mode == 2)  // state machine per lane, one CTA per 32x4 pixels
-	{
-		a.defer = prepare_defer_queue<ST, ALGO>(s);
-		if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-		else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-		launch_resume<ST, ALGO>(s, a);
+		// primary rays (one CTA per 32x4 pixels; mode 1: nested loops, mode 2: state machine), then the queued shadow rays, then the
+		// rays either kernel parked
+		if (prepare_shadow_queue(s, (size_t)grid.x * grid.y * grid.z * kRenderThreads, a) != VRM_OK) return;
+		if (mode == 1)
+		{
+			if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			launch_shadow<ST, ALGO, false>(s, a);
+		}
+		else
+		{
+			a.defer = prepare_defer_queue<ST, ALGO>(s);
+			if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			launch_shadow<ST, ALGO, true>(s, a);
+			launch_resume<ST, ALGO>(s, a);
+		}
 		return;
 	}
 	// persistent kernel: as many CTAs as fit on the device at once (a multiple of the SM count)
@@ -802,13 +967,28 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
 		s->statsRays = (uint64_t)W * H * nViews;
 	}
-	dim3 grid((W + kBlockW - 1) / kBlockW, (yEnd - yBase + kBlockH - 1) / kBlockH, nViews);
+	// A launch covers as many views as the shadow-ray queue (one record per pixel, worst case) and 32-bit pixel numbers allow
+	const uint64_t threadsPerView = (uint64_t)((W + kBlockW - 1) / kBlockW) * ((yEnd - yBase + kBlockH - 1) / kBlockH) * kRenderThreads;
+	constexpr uint64_t kQueueRecords = 32ull << 20;  // 1 GiB of records at most, unless a single view needs more
+	if (a.viewPixels >= (1ull << 32)) { s->lastError = "frame too large"; return VRM_ERR_INVALID; }
+	uint64_t chunkViews = kQueueRecords / threadsPerView;
+	if (chunkViews > ((1ull << 32) - 1) / a.viewPixels) chunkViews = ((1ull << 32) - 1) / a.viewPixels;
+	if (chunkViews < 1) chunkViews = 1;
 	const bool hash = s->storage == VRM_STORAGE_HASHTABLE, orig = algorithm == VRM_ALGO_ORIGINAL;
-	if (hash && orig) launch_render_t<kStorageHash, kAlgoOriginal>(s, a, grid);
-	else if (hash) launch_render_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
-	else if (orig) launch_render_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
-	else launch_render_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
-	VRM_CUDA(s, cudaGetLastError());
+	for (uint64_t v0 = 0; v0 < nViews; v0 += chunkViews)
+	{
+		const uint32_t nv = (uint32_t)(nViews - v0 < chunkViews ? nViews - v0 : chunkViews);
+		a.cams = d_cams + v0 * 15;
+		a.rgb = d_rgb + v0 * a.viewPixels * 3;
+		a.hits = d_hits ? d_hits + v0 * a.viewPixels * 4 : nullptr;
+		a.nViews = nv;
+		dim3 grid((W + kBlockW - 1) / kBlockW, (yEnd - yBase + kBlockH - 1) / kBlockH, nv);
+		if (hash && orig) launch_render_t<kStorageHash, kAlgoOriginal>(s, a, grid);
+		else if (hash) launch_render_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
+		else if (orig) launch_render_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
+		else launch_render_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
+		VRM_CUDA(s, cudaGetLastError());
+	}
 	if (yEnd == H) vrm_signal_completion(s, nViews);  // (a band launch signals with the frame's last band)
 	return VRM_OK;
 }
