@@ -470,7 +470,10 @@ def main():
                     "binding_roof": "instruction issue (the touched working set is L1/L2-resident: DRAM traffic is ~1 % of the algorithmic bytes)",
                     "issue": issue,
                     "l2": None if l2 is None else {"gather8_gbs": l2["gather8_gbs"], "gather8_loads_per_ns": l2["gather8_loads_per_ns"], "stream_gbs": l2["stream_gbs"],
-                                                   "working_set_bytes": l2["working_set_bytes"], "frac_of_gather_roof": achieved / l2["gather8_gbs"] if l2["gather8_gbs"] else None},
+                                                   "working_set_bytes": l2["working_set_bytes"],
+                                                   # every item of the byte model except the frame store is one load: loads per ns against the gather roof
+                                                   "achieved_loads_per_ns": (alg_bytes - 3 * WIDTH * HEIGHT) / 4 / (k_ms * 1e6),
+                                                   "frac_of_gather_roof": (alg_bytes - 3 * WIDTH * HEIGHT) / 4 / (k_ms * 1e6) / l2["gather8_loads_per_ns"] if l2["gather8_loads_per_ns"] else None},
                     "note": "SURVEY.md 8d per-ray model, with 4 B per region-table read (the table holds int32 here; the reference's 8-byte pointers would make it "
                             "+4 B per region read, ~+22 B per ray); traffic / issue figures come from the committed ncu capture of the single view (profiles/ncu_summary.json)"}
         line = {

@@ -92,12 +92,14 @@ struct ShadowArgs
 	unsigned int* ctl;
 	uint32_t cap;
 	uint32_t skipDead;     // 1: a record whose shaded colour is already black is not traced (0 * !shadow = 0); 0: trace everything (reference-comparable event counters)
-	uint8_t* rgb;
+	uint8_t* rgb;          // frame: the record's pixel number indexes RGB8 triples ...
+	uint32_t* colour;      // ... or (trace_rays) one uint32 colour per ray when this is not null
 	Stats* stats;
 	void* defer;
 };
 
-__device__ __forceinline__ void shadow_enqueue(const RenderArgs& a, bool want, const ShadowStart& ss, uint32_t pixel)
+template <class Args>
+__device__ __forceinline__ void shadow_enqueue(const Args& a, bool want, const ShadowStart& ss, uint32_t pixel)
 {
 	const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
 	if (m == 0u) return;
@@ -359,7 +361,12 @@ __global__ void __launch_bounds__(kShadowThreads, (FLAT ? VRM_SHADOW_MINBLOCKS :
 				if (ray.st == kStPark)
 				{
 					const int slot = ray.park(c);
-					if (slot >= 0) { park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (size_t)pixel, 0u); final = ss.lit; }  // the resume kernel writes the pixel
+					if (slot >= 0)  // the resume kernel writes the pixel
+					{
+						if (a.colour) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + pixel, 1u);
+						else park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (size_t)pixel, 0u);
+						final = ss.lit;
+					}
 					else { while (ray.st < kStDone) ray.template step<kPpOff>(c); final = ray.result; }
 				}
 				else final = ray.result;
@@ -372,8 +379,12 @@ __global__ void __launch_bounds__(kShadowThreads, (FLAT ? VRM_SHADOW_MINBLOCKS :
 		if (active && final != ss.lit)
 		{
 			// the light is blocked: the shaded colour the render kernel stored becomes black
-			uint8_t* px = a.rgb + 3 * (size_t)pixel;
-			px[0] = (uint8_t)(final >> 16); px[1] = (uint8_t)((final >> 8) & 0xFF); px[2] = (uint8_t)(final & 0xFF);
+			if (a.colour) a.colour[pixel] = final;
+			else
+			{
+				uint8_t* px = a.rgb + 3 * (size_t)pixel;
+				px[0] = (uint8_t)(final >> 16); px[1] = (uint8_t)((final >> 8) & 0xFF); px[2] = (uint8_t)(final & 0xFF);
+			}
 		}
 	}
 	flush_stats<STATS>(c, a.stats);
@@ -491,6 +502,10 @@ struct TraceArgs
 	void* defer;
 	uint32_t* parkBits;    // lean kernels: one bit per ray that must be re-traced by resume_lean_trace_kernel
 	unsigned int* parkCtl;
+	unsigned long long first;  // first ray of this launch (a ray list is traced in launches of at most 2^30 rays: 32-bit queue records)
+	int4* shadowItems;     // shadow-ray queue, as in RenderArgs; the record's pixel field is the ray's index minus `first`
+	unsigned int* shadowCtl;
+	uint32_t shadowCap;
 };
 
 // Incoherent rays are latency-bound: occupancy is worth more than a few spilled registers (measured, 1024^3 shells, 8.3 M rays:
@@ -504,7 +519,9 @@ struct TraceArgs
 template <int ST, int ALGO, bool STATS, bool FLATLOOP>
 __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MINBLOCKS : VRM_TRACE_LA_MINBLOCKS) trace_kernel(const TraceArgs a)
 {
-	unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	// PRIMARY phase of caller-supplied rays (rayMarchVoxelScene[LongestAxis] called per ray); a hit is shaded and its
+	// shadow ray queued for shadow_kernel, exactly as in render_kernel.  Incoherent rays: every lane runs its own loop.
+	const unsigned long long i = a.first + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
@@ -512,30 +529,14 @@ __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MI
 	c.hitOut = nullptr;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
-	if constexpr (FLATLOOP && VRM_TRACE_HIT_BARRIER != 0 && ST == kStorageVcs && ALGO != kAlgoOriginal)
+	bool hit = false;
+	ShadowStart ss;
+	ss.hitW[0] = ss.hitW[1] = ss.hitW[2] = 0.0f; ss.regW[0] = ss.regW[1] = ss.regW[2] = 0; ss.lit = 0u; ss.la = 0;
+	if (i < a.n)
 	{
-		// warp-cooperative state machine with the hit barrier (see render_kernel); lanes past the end of the ray list idle
-		const bool active = i < a.n;
-		float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
-		if (active)
-		{
-			for (int k = 0; k < 3; k++) { o[k] = __ldg(a.rays + 6 * i + k); d[k] = __ldg(a.rays + 6 * i + 3 + k); }
-			if (a.hits)
-			{
-				c.hitOut = a.hits + 4 * i;
-				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
-			}
-		}
-		c.deferQueue = a.defer;
-		int slot;
-		const uint32_t colour = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, active, o, d, a.scale, slot);
-		if (active) a.colour[i] = colour;
-		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + i, 1u);
-	}
-	else if (i < a.n)
-	{
-		float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
-		float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
+		const float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
+		const float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
+		uint32_t colour = 0;
 		if constexpr (FLATLOOP)
 		{
 			if (a.hits)
@@ -544,16 +545,27 @@ __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MI
 				*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
 			}
 			c.deferQueue = a.defer;
-			int slot;
-			a.colour[i] = march_scene_flat<ST, ALGO, STATS, kPpDefer>(c, o, d, a.scale, slot);
-			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + i, 1u);
+			FlatRay<ST, ALGO, STATS> ray;
+			ray.start_primary(c, o, d, a.scale);
+			while (ray.st <= kStHead) ray.template step_marching<kPpDefer>(c);
+			if (ray.st == kStHit) { ray.shade_hit(c, ss); hit = true; colour = ss.lit; }
+			else if (ray.st == kStPark)
+			{
+				const int slot = ray.park(c);
+				if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + i, 1u);
+				else { while (ray.st < kStDone) ray.template step<kPpOff>(c); colour = ray.result; }
+			}
+			else colour = ray.result;
 		}
 		else
 		{
-			a.colour[i] = march_scene<ST, ALGO, STATS>(c, o, d, a.scale);
+			hit = march_scene_primary<ST, ALGO, STATS>(c, o, d, a.scale, ss);
+			colour = hit ? ss.lit : 0u;
 			if (a.hits) reinterpret_cast<int4*>(a.hits)[i] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 		}
+		a.colour[i] = colour;
 	}
+	if (a.shadowItems) shadow_enqueue(a, hit, ss, (uint32_t)(i - a.first));
 	flush_stats<STATS>(c, a.stats);
 }
 
@@ -766,10 +778,11 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 	a.stats = s->statsEnabled ? s->d_stats : nullptr;
 	a.defer = nullptr;
 	a.parkBits = nullptr; a.parkCtl = nullptr;
+	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0;
 }
 
 // Shadow-ray queue of the handle: room for `records` records (grow-only), counters zeroed on the stream.
-int prepare_shadow_queue(vrm_scene* s, size_t records, RenderArgs& a)
+template <class Args> int prepare_shadow_queue(vrm_scene* s, size_t records, Args& a)
 {
 	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0;
 	if (!s->light.useShadows) return VRM_OK;
@@ -785,7 +798,7 @@ int prepare_shadow_queue(vrm_scene* s, size_t records, RenderArgs& a)
 	return VRM_OK;
 }
 
-template <int ST, int ALGO, bool FLAT> void launch_shadow(vrm_scene* s, const RenderArgs& a)
+template <int ST, int ALGO, bool FLAT, class Args> void launch_shadow(vrm_scene* s, const Args& a, uint8_t* rgb, uint32_t* colour)
 {
 	if (!a.shadowItems) return;
 	ShadowArgs b;
@@ -793,7 +806,7 @@ template <int ST, int ALGO, bool FLAT> void launch_shadow(vrm_scene* s, const Re
 	b.translation[0] = a.translation[0]; b.translation[1] = a.translation[1]; b.translation[2] = a.translation[2];
 	b.items = a.shadowItems; b.ctl = a.shadowCtl; b.cap = a.shadowCap;
 	b.skipDead = s->statsMode == 1 ? 0u : 1u;
-	b.rgb = a.rgb; b.stats = a.stats; b.defer = a.defer;
+	b.rgb = rgb; b.colour = colour; b.stats = a.stats; b.defer = a.defer;
 	static int blocksPerSm[2] = {0, 0};  // per instantiation (function template static)
 	int& bps = blocksPerSm[s->statsEnabled ? 1 : 0];
 	if (bps == 0)
@@ -886,14 +899,14 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 		{
 			if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			launch_shadow<ST, ALGO, false>(s, a);
+			launch_shadow<ST, ALGO, false>(s, a, a.rgb, nullptr);
 		}
 		else
 		{
 			a.defer = prepare_defer_queue<ST, ALGO>(s);
 			if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			launch_shadow<ST, ALGO, true>(s, a);
+			launch_shadow<ST, ALGO, true>(s, a, a.rgb, nullptr);
 			launch_resume<ST, ALGO>(s, a);
 		}
 		return;
@@ -927,17 +940,21 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 		resume_lean_kernel<ST, ALGO, false, TraceArgs><<<(unsigned)s->numSms, kResumeLeanThreads, 0, s->stream>>>(a, a.n);
 		return;
 	}
+	if (prepare_shadow_queue(s, (size_t)grid * 256, a) != VRM_OK) return;
+	uint32_t* colour = a.colour + a.first;
 	if (mode == 2)
 	{
 		a.defer = prepare_defer_queue<ST, ALGO>(s);
 		if (s->statsEnabled) trace_kernel<ST, ALGO, true, true><<<grid, 256, 0, s->stream>>>(a);
 		else trace_kernel<ST, ALGO, false, true><<<grid, 256, 0, s->stream>>>(a);
+		launch_shadow<ST, ALGO, true>(s, a, nullptr, colour);
 		launch_resume<ST, ALGO>(s, a);
 	}
 	else
 	{
 		if (s->statsEnabled) trace_kernel<ST, ALGO, true, false><<<grid, 256, 0, s->stream>>>(a);
 		else trace_kernel<ST, ALGO, false, false><<<grid, 256, 0, s->stream>>>(a);
+		launch_shadow<ST, ALGO, false>(s, a, nullptr, colour);
 	}
 }
 
@@ -1007,13 +1024,20 @@ int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float*
 		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
 		s->statsRays = n;
 	}
-	unsigned grid = (unsigned)((n + 255) / 256);
 	const bool hash = s->storage == VRM_STORAGE_HASHTABLE, orig = algorithm == VRM_ALGO_ORIGINAL;
-	if (hash && orig) launch_trace_t<kStorageHash, kAlgoOriginal>(s, a, grid);
-	else if (hash) launch_trace_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
-	else if (orig) launch_trace_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
-	else launch_trace_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
-	VRM_CUDA(s, cudaGetLastError());
+	const uint64_t kChunk = s->renderMode == 3 ? n : (32ull << 20);  // rays per launch: the shadow-ray queue holds one record per ray at most (1 GiB); the lean test kernels take the list whole
+	for (uint64_t first = 0; first < n; first += kChunk)
+	{
+		const uint64_t m = n - first < kChunk ? n - first : kChunk;
+		a.first = first;
+		const unsigned grid = (unsigned)((m + 255) / 256);
+		a.n = first + m;
+		if (hash && orig) launch_trace_t<kStorageHash, kAlgoOriginal>(s, a, grid);
+		else if (hash) launch_trace_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
+		else if (orig) launch_trace_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
+		else launch_trace_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
+		VRM_CUDA(s, cudaGetLastError());
+	}
 	return VRM_OK;
 }
 
