@@ -3,7 +3,7 @@
 
     python tools/ab_variants.py main old:mode=2 cta128 mb3@vcs:longestaxis
 
-A spec is  <variant>[:mode=<VRM_RENDER_MODE>][@<storage>:<algo>,...] ; `main` is the product library.  Each spec runs in its own
+A spec is  <variant>[:mode=<VRM_RENDER_MODE>][:shadow=<VRM_SHADOW_FORM>][@<storage>:<algo>,...] ; `main` is the product library.  Each spec runs in its own
 process (the library path is read at import).  Prints one line per (spec, combination) and writes gpurun_out/ab.json."""
 import json
 import os
@@ -29,6 +29,8 @@ def main():
             k, v = kv.split("=")
             if k == "mode":
                 env["VRM_RENDER_MODE"] = v
+            elif k == "shadow":
+                env["VRM_SHADOW_FORM"] = v
         if name != "main":
             env["VRM_B200_LIB"] = os.path.join(ROOT, "voxelraymarcher_b200", "variants", f"libvrm_{name}.so")
         out = os.path.join(ROOT, "gpurun_out", f"ab_{spec.replace(':', '_').replace('@', '_').replace(',', '_').replace('=', '')}.json")

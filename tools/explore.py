@@ -59,13 +59,25 @@ def main():
         for st, algo in combos:
             if st != storage:
                 continue
+            # device-resident frame, CUDA events on the launching stream, L2 flushed between launches (as bench.py does); the first
+            # render goes through the host path once for the hit fraction
+            import torch
+            r = s.render(W, H, algo, cam, scale=scale, want_hits=True)
+            hitfrac = float(r["hits"][..., 3].mean())
+            cur = torch.cuda.current_stream()
+            s.set_stream(cur.cuda_stream)
+            fb = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda:0")
+            flush = torch.zeros(512 << 20, dtype=torch.uint8, device="cuda:0")
             times = []
             for i in range(a.iters + 2):
-                r = s.render(W, H, algo, cam, scale=scale, want_hits=(i == 0))
-                if i == 0:
-                    hitfrac = float(r["hits"][..., 3].mean())
+                flush.add_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur); s.render_device(W, H, algo, cam, fb.data_ptr(), scale=scale); e1.record(cur)
+                torch.cuda.synchronize()
                 if i >= 2:
-                    times.append(r["kernel_ms"])
+                    times.append(e0.elapsed_time(e1))
+            del flush
+            s.reset_stream()
             s.set_statistics(True)
             s.render(W, H, algo, cam, scale=scale)
             stats = s.get_statistics()

@@ -182,6 +182,7 @@ int vrm_scene_create(int device, vrm_scene** out)
 
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->numSms, cudaDevAttrMultiProcessorCount, device);
 	if (const char* mode = getenv("VRM_RENDER_MODE")) s->renderMode = atoi(mode);
+	if (const char* form = getenv("VRM_SHADOW_FORM")) { const int f = atoi(form); if (f >= 0 && f <= 2) s->shadowForm = f; }
 	if (const char* lp = getenv("VRM_L2_PERSIST")) s->l2Persist = atoi(lp) != 0;
 	if (const char* bb = getenv("VRM_VIEW_BATCH_BYTES")) { long long v = atoll(bb); if (v > 0) s->viewBatchBytes = (size_t)v; }
 	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }

@@ -71,6 +71,7 @@ struct RenderArgs
 	int4* shadowItems;     // shadow-ray queue (two int4 per record), null when shadows are off
 	unsigned int* shadowCtl;  // {records queued, next record to claim}
 	uint32_t shadowCap;
+	uint32_t skipDead;     // 1: a hit whose shaded colour is already black queues no shadow ray (0 * !shadow = 0)
 };
 
 // ---- shadow-ray queue ------------------------------------------------------------------------------------------------------------
@@ -99,8 +100,9 @@ struct ShadowArgs
 };
 
 template <class Args>
-__device__ __forceinline__ void shadow_enqueue(const Args& a, bool want, const ShadowStart& ss, uint32_t pixel)
+__device__ __forceinline__ void shadow_enqueue(const Args& a, bool hit, const ShadowStart& ss, uint32_t pixel)
 {
+	const bool want = hit && !(a.skipDead && ss.lit == 0u);
 	const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
 	if (m == 0u) return;
 	const unsigned lane = threadIdx.x & 31u;
@@ -349,7 +351,6 @@ __global__ void __launch_bounds__(kShadowThreads, (FLAT ? VRM_SHADOW_MINBLOCKS :
 			pixel = (uint32_t)v1.z;
 			ss.lit = (uint32_t)v1.w & 0x7FFFFFFFu;
 			ss.la = ((uint32_t)v1.w >> 31) ? 1 : 0;
-			if (a.skipDead && ss.lit == 0u) active = false;  // colour * !shadow with colour == 0
 		}
 		uint32_t final = ss.lit;
 		if constexpr (FLAT)
@@ -386,6 +387,94 @@ __global__ void __launch_bounds__(kShadowThreads, (FLAT ? VRM_SHADOW_MINBLOCKS :
 				px[0] = (uint8_t)(final >> 16); px[1] = (uint8_t)((final >> 8) & 0xFF); px[2] = (uint8_t)(final & 0xFF);
 			}
 		}
+	}
+	flush_stats<STATS>(c, a.stats);
+}
+
+// The same queue walked with LANE-LEVEL REFILL: a lane whose shadow ray has ended takes the next record as soon as enough lanes of its
+// warp are free (one atomicAdd per refill), so short (blocked) and long (light reaches the sky) shadow rays no longer make a warp
+// wait for its longest one.  Shadow rays share one direction and consecutive records are neighbouring pixels, so the mixture a warp
+// holds stays coherent.  The state machine of vrm_flat.cuh for every combination (one micro-step per pass).
+#ifndef VRM_SHADOW_REFILL_MIN
+#define VRM_SHADOW_REFILL_MIN 8
+#endif
+template <int ST, int ALGO, bool STATS>
+__global__ void __launch_bounds__(kShadowThreads, (ALGO == kAlgoOriginal ? 6 : VRM_SHADOW_MINBLOCKS) * 256 / kShadowThreads) shadow_refill_kernel(const ShadowArgs a)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned queued = a.ctl[0];
+	const unsigned count = queued < a.cap ? queued : a.cap;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	c.deferQueue = a.defer;
+	FlatRay<ST, ALGO, STATS> ray;
+	ray.st = kStDone; ray.result = 0u;
+	bool have = false, dry = false;  // dry is warp-uniform: the queue has no unclaimed record left
+	uint32_t pixel = 0, lit = 0;
+	for (;;)
+	{
+		// a ray that ended in the last pass: its pixel keeps the shaded colour or turns black
+		if (have && ray.st >= kStDone)
+		{
+			uint32_t final = ray.result;
+			bool write = true;
+			if (ray.st == kStPark)
+			{
+				const int slot = ray.park(c);
+				if (slot >= 0)  // the resume kernel writes the pixel
+				{
+					if (a.colour) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + pixel, 1u);
+					else park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * (size_t)pixel, 0u);
+					write = false;
+				}
+				else { while (ray.st < kStDone) ray.template step<kPpOff>(c); final = ray.result; }
+			}
+			if (write && final != lit)
+			{
+				if (a.colour) a.colour[pixel] = final;
+				else
+				{
+					uint8_t* px = a.rgb + 3 * (size_t)pixel;
+					px[0] = (uint8_t)(final >> 16); px[1] = (uint8_t)((final >> 8) & 0xFF); px[2] = (uint8_t)(final & 0xFF);
+				}
+			}
+			have = false;
+			ray.st = kStDone;
+		}
+		const unsigned freeMask = __ballot_sync(0xFFFFFFFFu, !have);
+		const int nFree = __popc(freeMask);
+		if (!dry && (nFree >= VRM_SHADOW_REFILL_MIN || nFree == 32))
+		{
+			unsigned base = 0;
+			const int leader = __ffs(freeMask) - 1;
+			if ((int)lane == leader) base = atomicAdd(a.ctl + 1, (unsigned)nFree);
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (base + (unsigned)nFree >= count) dry = true;
+			if (!have)
+			{
+				const unsigned i = base + __popc(freeMask & ((1u << lane) - 1u));
+				if (i < count)
+				{
+					const int4 v0 = __ldg(a.items + 2 * (size_t)i), v1 = __ldg(a.items + 2 * (size_t)i + 1);
+					ShadowStart ss;
+					ss.hitW[0] = __int_as_float(v0.x); ss.hitW[1] = __int_as_float(v0.y); ss.hitW[2] = __int_as_float(v0.z);
+					ss.regW[0] = v0.w; ss.regW[1] = v1.x; ss.regW[2] = v1.y;
+					pixel = (uint32_t)v1.z;
+					lit = (uint32_t)v1.w & 0x7FFFFFFFu;
+					ss.lit = lit;
+					ss.la = ((uint32_t)v1.w >> 31) ? 1 : 0;
+					ray.start_shadow(c, ss);
+					have = true;
+				}
+			}
+		}
+		if (!__any_sync(0xFFFFFFFFu, have)) break;  // nothing in flight: the refill above found the queue empty
+		warp_march_pass<ST, ALGO, STATS, kPpDefer>(c, ray);
 	}
 	flush_stats<STATS>(c, a.stats);
 }
@@ -506,6 +595,7 @@ struct TraceArgs
 	int4* shadowItems;     // shadow-ray queue, as in RenderArgs; the record's pixel field is the ray's index minus `first`
 	unsigned int* shadowCtl;
 	uint32_t shadowCap;
+	uint32_t skipDead;
 };
 
 // Incoherent rays are latency-bound: occupancy is worth more than a few spilled registers (measured, 1024^3 shells, 8.3 M rays:
@@ -778,13 +868,13 @@ template <class Args> void fill_common(Args& a, const vrm_scene* s, const float*
 	a.stats = s->statsEnabled ? s->d_stats : nullptr;
 	a.defer = nullptr;
 	a.parkBits = nullptr; a.parkCtl = nullptr;
-	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0;
+	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0; a.skipDead = 0;
 }
 
 // Shadow-ray queue of the handle: room for `records` records (grow-only), counters zeroed on the stream.
 template <class Args> int prepare_shadow_queue(vrm_scene* s, size_t records, Args& a)
 {
-	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0;
+	a.shadowItems = nullptr; a.shadowCtl = nullptr; a.shadowCap = 0; a.skipDead = 0;
 	if (!s->light.useShadows) return VRM_OK;
 	if (!s->d_shadowCtl) VRM_CUDA(s, cudaMalloc(&s->d_shadowCtl, 2 * sizeof(unsigned int)));
 	if (s->shadowCap < records)
@@ -795,29 +885,34 @@ template <class Args> int prepare_shadow_queue(vrm_scene* s, size_t records, Arg
 	}
 	VRM_CUDA(s, cudaMemsetAsync(s->d_shadowCtl, 0, 2 * sizeof(unsigned int), s->stream));
 	a.shadowItems = static_cast<int4*>(s->d_shadowItems); a.shadowCtl = s->d_shadowCtl; a.shadowCap = (uint32_t)records;
+	a.skipDead = s->statsMode == 1 ? 0u : 1u;  // reference-comparable event counters need every shadow ray traced, as the reference does
 	return VRM_OK;
 }
 
-template <int ST, int ALGO, bool FLAT, class Args> void launch_shadow(vrm_scene* s, const Args& a, uint8_t* rgb, uint32_t* colour)
+// form: 0 nested loops / 1 state machine, a warp claims 32 consecutive records at a time; 2 state machine with lane-level refill
+template <int ST, int ALGO, class Args> void launch_shadow(vrm_scene* s, const Args& a, uint8_t* rgb, uint32_t* colour, int form)
 {
 	if (!a.shadowItems) return;
 	ShadowArgs b;
 	b.sv = a.sv; b.light = a.light; b.lw = a.lw;
 	b.translation[0] = a.translation[0]; b.translation[1] = a.translation[1]; b.translation[2] = a.translation[2];
 	b.items = a.shadowItems; b.ctl = a.shadowCtl; b.cap = a.shadowCap;
-	b.skipDead = s->statsMode == 1 ? 0u : 1u;
+	b.skipDead = a.skipDead;
 	b.rgb = rgb; b.colour = colour; b.stats = a.stats; b.defer = a.defer;
-	static int blocksPerSm[2] = {0, 0};  // per instantiation (function template static)
-	int& bps = blocksPerSm[s->statsEnabled ? 1 : 0];
+	static int blocksPerSm[3][2] = {};  // per instantiation (function template static)
+	int& bps = blocksPerSm[form][s->statsEnabled ? 1 : 0];
+	const bool st = s->statsEnabled;
 	if (bps == 0)
 	{
-		if (s->statsEnabled) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, true, FLAT>, kShadowThreads, 0);
-		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, false, FLAT>, kShadowThreads, 0);
+		if (form == 2) { if (st) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_refill_kernel<ST, ALGO, true>, kShadowThreads, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_refill_kernel<ST, ALGO, false>, kShadowThreads, 0); }
+		else if (form == 1) { if (st) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, true, true>, kShadowThreads, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, false, true>, kShadowThreads, 0); }
+		else { if (st) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, true, false>, kShadowThreads, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, shadow_kernel<ST, ALGO, false, false>, kShadowThreads, 0); }
 		if (bps < 1) bps = 1;
 	}
 	const unsigned blocks = (unsigned)(s->numSms * bps);   // one resident wave: a multiple of the SM count
-	if (s->statsEnabled) shadow_kernel<ST, ALGO, true, FLAT><<<blocks, kShadowThreads, 0, s->stream>>>(b);
-	else shadow_kernel<ST, ALGO, false, FLAT><<<blocks, kShadowThreads, 0, s->stream>>>(b);
+	if (form == 2) { if (st) shadow_refill_kernel<ST, ALGO, true><<<blocks, kShadowThreads, 0, s->stream>>>(b); else shadow_refill_kernel<ST, ALGO, false><<<blocks, kShadowThreads, 0, s->stream>>>(b); }
+	else if (form == 1) { if (st) shadow_kernel<ST, ALGO, true, true><<<blocks, kShadowThreads, 0, s->stream>>>(b); else shadow_kernel<ST, ALGO, false, true><<<blocks, kShadowThreads, 0, s->stream>>>(b); }
+	else { if (st) shadow_kernel<ST, ALGO, true, false><<<blocks, kShadowThreads, 0, s->stream>>>(b); else shadow_kernel<ST, ALGO, false, false><<<blocks, kShadowThreads, 0, s->stream>>>(b); }
 }
 
 constexpr unsigned int kDeferCapacity = 16384;  // parked rays per launch (a 4K frame of the 2048^3 orbit parks a few dozen); VRM_DEFER_CAPACITY overrides (tests)
@@ -899,14 +994,14 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 		{
 			if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			launch_shadow<ST, ALGO, false>(s, a, a.rgb, nullptr);
+			launch_shadow<ST, ALGO>(s, a, a.rgb, nullptr, s->shadowForm >= 0 ? s->shadowForm : 0);
 		}
 		else
 		{
 			a.defer = prepare_defer_queue<ST, ALGO>(s);
 			if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			launch_shadow<ST, ALGO, true>(s, a, a.rgb, nullptr);
+			launch_shadow<ST, ALGO>(s, a, a.rgb, nullptr, s->shadowForm >= 0 ? s->shadowForm : 1);
 			launch_resume<ST, ALGO>(s, a);
 		}
 		return;
@@ -947,14 +1042,14 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 		a.defer = prepare_defer_queue<ST, ALGO>(s);
 		if (s->statsEnabled) trace_kernel<ST, ALGO, true, true><<<grid, 256, 0, s->stream>>>(a);
 		else trace_kernel<ST, ALGO, false, true><<<grid, 256, 0, s->stream>>>(a);
-		launch_shadow<ST, ALGO, true>(s, a, nullptr, colour);
+		launch_shadow<ST, ALGO>(s, a, nullptr, colour, s->shadowForm >= 0 ? s->shadowForm : 1);
 		launch_resume<ST, ALGO>(s, a);
 	}
 	else
 	{
 		if (s->statsEnabled) trace_kernel<ST, ALGO, true, false><<<grid, 256, 0, s->stream>>>(a);
 		else trace_kernel<ST, ALGO, false, false><<<grid, 256, 0, s->stream>>>(a);
-		launch_shadow<ST, ALGO, false>(s, a, nullptr, colour);
+		launch_shadow<ST, ALGO>(s, a, nullptr, colour, s->shadowForm >= 0 ? s->shadowForm : 0);
 	}
 }
 
