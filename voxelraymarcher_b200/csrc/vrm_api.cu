@@ -201,7 +201,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	vrm_free_async(s, s->d_regionMinMax); s->d_regionMinMax = nullptr;
 	vrm_free_structure(s);
 	cudaStreamSynchronize(s->stream);
-	cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer); cudaFree(s->d_parkBits); cudaFree(s->d_parkCtl); cudaFree(s->d_gather); cudaFree(s->d_shadowItems); cudaFree(s->d_shadowCtl); if (s->h_stage) cudaFreeHost(s->h_stage); for (auto& e : s->evBand) if (e) cudaEventDestroy(e);
+	cudaFree(s->d_hits); cudaFree(s->d_cams); cudaFree(s->d_io); cudaFree(s->d_stats); cudaFree(s->d_queue); cudaFree(s->d_defer); cudaFree(s->d_parkBits); cudaFree(s->d_parkCtl); cudaFree(s->d_gather); cudaFree(s->d_shadowItems); cudaFree(s->d_shadowCtl); cudaFree(s->d_localFrame); if (s->h_stage) cudaFreeHost(s->h_stage); for (auto& e : s->evBand) if (e) cudaEventDestroy(e);
 	if (s->h_cams) cudaFreeHost(s->h_cams);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);
@@ -401,7 +401,7 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
 	constexpr int kMaxBands = 8;
 	int bands = 1;
-	if (stageRgb) { bands = (int)(px * 3 / (size_t(2) << 20)); if (bands < 1) bands = 1; if (bands > kMaxBands) bands = kMaxBands; }  // >= 2 MB per band
+	if (stageRgb) { bands = (int)(px * 3 / (size_t(6) << 20)); if (bands < 1) bands = 1; if (bands > 4) bands = 4; }  // >= 6 MB per band, four bands at most (every band is a launch sequence of its own)
 	uint32_t bandEnd[kMaxBands];
 	for (int b = 0; b < bands; b++) bandEnd[b] = b == bands - 1 ? height : (uint32_t)(((uint64_t)height * (b + 1) / bands + 7) & ~7ull);
 	if (stageRgb) for (int b = 0; b < bands; b++) if (!s->evBand[b]) VRM_CUDA(s, cudaEventCreateWithFlags(&s->evBand[b], cudaEventDisableTiming));

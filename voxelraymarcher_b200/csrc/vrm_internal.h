@@ -88,6 +88,7 @@ struct vrm_scene
 	void* d_shadowItems = nullptr;    size_t shadowCap = 0;
 	unsigned int* d_shadowCtl = nullptr;
 
+	uint8_t* d_localFrame = nullptr;  size_t localFrameBytes = 0;  // frames of a queue-pipeline launch whose destination is not local memory
 	int shadowForm = -1;              // shadow kernel: -1 per-combination default, 0 nested loops, 1 state machine, 2 state machine with lane-level refill (VRM_SHADOW_FORM)
 	int statsMode = 0;                // 0 off, 1 event counters comparable with the reference (every shadow ray traced), 2 counters of the work as executed
 	bool statsEnabled = false;

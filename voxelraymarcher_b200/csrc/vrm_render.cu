@@ -57,6 +57,7 @@ struct RenderArgs
 	const float* cams;  // nViews x 15
 	uint32_t W, H;
 	size_t viewPixels;     // pixel slots between the outputs of consecutive views (W * H, or a multiple of it for interleaved view sharding)
+	size_t rgbViewPixels;  // the same for the frame array `rgb` alone (it differs when the frames are rendered into the handle's local buffer first)
 	float invW, invH;      // RN(1 / W), RN(1 / H) (host): exact division by a constant in primary_ray_flat
 	uint32_t rowWordsOk;   // 1 when every 32-pixel row segment starts on a 4-byte boundary (W * 3 % 4 == 0 and an aligned base)
 	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
@@ -196,9 +197,12 @@ __global__ void __launch_bounds__(kResumeThreads) resume_kernel(const ResumeArgs
 	}
 }
 
-template <int ST, int ALGO, bool STATS, bool FLATLOOP>
-__global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? (ALGO == kAlgoOriginal ? 6 : 5) : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
+// FORM 0: nested loops, primary rays only (shadow rays go to the queue); 1: state machine, primary rays only; 2: state machine with the
+// shadow ray in the kernel behind a hit barrier (march_scene_flat_warp) -- the default for VCS + longest axis, see launch_render_t
+template <int ST, int ALGO, bool STATS, int FORM>
+__global__ void __launch_bounds__(kRenderThreads, ((FORM != 0 && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? (ALGO == kAlgoOriginal ? 6 : 5) : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
 {
+	constexpr bool FLATLOOP = FORM != 0;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lx = (warp % kBlockTilesX) * kTileW + (lane & (kTileW - 1)), ly = (warp / kBlockTilesX) * kTileH + (lane / kTileW);
 	const uint32_t x0 = blockIdx.x * kBlockW, y0 = a.yBase + blockIdx.y * kBlockH;
@@ -219,7 +223,8 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 	bool hit = false;
 	ShadowStart ss;
 	ss.hitW[0] = ss.hitW[1] = ss.hitW[2] = 0.0f; ss.regW[0] = ss.regW[1] = ss.regW[2] = 0; ss.lit = 0u; ss.la = 0;
-	const size_t pixel = (size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x;
+	const size_t pixel = (size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x;        // hit map slot
+	const size_t pixelOut = (size_t)blockIdx.z * a.rgbViewPixels + (size_t)y * a.W + x;  // frame slot (also the shadow record's)
 	if constexpr (FLATLOOP)
 	{
 		// warp-cooperative state machine (vrm_flat.cuh): every lane takes part in the votes, lanes outside the image just idle
@@ -239,6 +244,15 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 			}
 		}
 		c.deferQueue = a.defer;
+		if constexpr (FORM == 2)
+		{
+			// both phases here: lanes that hit wait at the hit barrier, the tile then shades and walks its shadow rays together
+			int slot;
+			color = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, slot);
+			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * pixelOut, 0u);
+		}
+		else
+		{
 		FlatRay<ST, ALGO, STATS> ray;
 		march_primary_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, ray);
 		if (ray.st == kStHit)
@@ -251,10 +265,11 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		{
 			// region-face ping-pong (vrm_flat.cuh): the ray goes to the resume kernel, which finishes it -- shadow ray included
 			const int slot = ray.park(c);
-			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * pixel, 0u);
+			if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.rgb + 3 * pixelOut, 0u);
 			else { while (ray.st < kStDone) ray.template step<kPpOff>(c); color = ray.result; }  // queue full: crawl on like the reference
 		}
 		else color = ray.result;
+		}
 	}
 	else if (inside)
 	{
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		if (a.hits) reinterpret_cast<int4*>(a.hits)[pixel] = make_int4(c.hit[0], c.hit[1], c.hit[2], c.hit[3]);
 	}
 	// the shadow ray of a hit goes to the queue; without shadows (USE_SHADOWS false, Main.cu:41) the shaded colour is final
-	if (a.shadowItems) shadow_enqueue(a, hit, ss, (uint32_t)pixel);
+	if constexpr (FORM != 2) { if (a.shadowItems) shadow_enqueue(a, hit, ss, (uint32_t)pixelOut); }
 	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
 #if VRM_WARP_STORE
 	// per-warp staging: each warp writes its own 8x4 tile as four 24-byte row segments, no CTA barrier
@@ -284,7 +299,7 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		if (lane < kTileH * (kTileW * 3 / 4))
 		{
 			const uint32_t row = lane / (kTileW * 3 / 4), w = lane % (kTileW * 3 / 4);
-			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.viewPixels + (size_t)(ty0 + row) * a.W + tx0) * 3);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.rgbViewPixels + (size_t)(ty0 + row) * a.W + tx0) * 3);
 			dst[w] = mine[row][w];
 		}
 	}
@@ -298,14 +313,14 @@ __global__ void __launch_bounds__(kRenderThreads, ((FLATLOOP && ALGO != kAlgoOri
 		if (threadIdx.x < kBlockH * (kBlockW * 3 / 4))
 		{
 			const uint32_t row = threadIdx.x / (kBlockW * 3 / 4), w = threadIdx.x % (kBlockW * 3 / 4);
-			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.viewPixels + (size_t)(y0 + row) * a.W + x0) * 3);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.rgbViewPixels + (size_t)(y0 + row) * a.W + x0) * 3);
 			dst[w] = staged[row][w];
 		}
 	}
 #endif
 	else if (inside)
 	{
-		size_t p = (size_t)blockIdx.z * a.viewPixels + (size_t)y * a.W + x;
+		const size_t p = pixelOut;
 		a.rgb[3 * p] = (uint8_t)(color >> 16);
 		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
 		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
@@ -972,9 +987,12 @@ int prepare_park(vrm_scene* s, unsigned long long totalRays, uint32_t** bits, un
 
 template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim3 grid)
 {
-	// Which form of the traversal runs is a measured choice per combination (512^3 terrain, 4K, B200):
-	// the per-lane state machine wins where cluster jumps nest inside the longest-axis loop (VCS + longest axis: 1.50 ms
-	// vs 2.9 ms nested); the nested loops win elsewhere (VCS + original 1.05 vs 1.16 ms, hash table 2.95 / 3.08 vs 3.45 / 3.94 ms).  VRM_RENDER_MODE=0|1|2 forces one form for A/B runs.
+	// Which form runs is a measured choice per combination (512^3 terrain, 4K, B200; DESIGN.md 3.2, profiles/r02e_ab.json):
+	//   VCS + longest axis: state machine with the shadow ray in the kernel behind a hit barrier (mode 2: 1.50 ms; with the shadow-ray
+	//   queue, mode 4: 1.54 ms -- its shadow rays mix head / jump / test phases whichever way they are grouped);
+	//   every other combination: nested loops for the primary rays + shadow-ray queue (mode 1: hash table 2.39 / 2.70 ms, VCS +
+	//   original 0.89 ms, against 2.94 / 3.09 / 1.04 ms with the shadow ray in the kernel).
+	// VRM_RENDER_MODE=0|1|2|3|4 forces one form for A/B runs.
 	int mode = s->renderMode >= 0 ? s->renderMode : ((ST == kStorageVcs && ALGO != kAlgoOriginal) ? 2 : 1);
 	if (mode == 3 && s->statsEnabled) mode = 2;  // the event counters live in the generic machine
 	if (mode == 3)  // lean state machine (vrm_lean.cuh) + re-trace of the rays it parked
@@ -985,22 +1003,30 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 		resume_lean_kernel<ST, ALGO, true, RenderArgs><<<(unsigned)s->numSms, kResumeLeanThreads, 0, s->stream>>>(a, totalRays);
 		return;
 	}
-	if (mode == 1 || mode == 2)
+	if (mode == 2)  // state machine, both phases in one kernel (hit barrier) + the rays it parked
 	{
-		// primary rays (one CTA per 32x4 pixels; mode 1: nested loops, mode 2: state machine), then the queued shadow rays, then the
+		a.defer = prepare_defer_queue<ST, ALGO>(s);
+		if (s->statsEnabled) render_kernel<ST, ALGO, true, 2><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		else render_kernel<ST, ALGO, false, 2><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		launch_resume<ST, ALGO>(s, a);
+		return;
+	}
+	if (mode == 1 || mode == 4)
+	{
+		// primary rays (one CTA per 32x4 pixels; mode 1: nested loops, mode 4: state machine), then the queued shadow rays, then the
 		// rays either kernel parked
 		if (prepare_shadow_queue(s, (size_t)grid.x * grid.y * grid.z * kRenderThreads, a) != VRM_OK) return;
 		if (mode == 1)
 		{
-			if (s->statsEnabled) render_kernel<ST, ALGO, true, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			else render_kernel<ST, ALGO, false, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			if (s->statsEnabled) render_kernel<ST, ALGO, true, 0><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else render_kernel<ST, ALGO, false, 0><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			launch_shadow<ST, ALGO>(s, a, a.rgb, nullptr, s->shadowForm >= 0 ? s->shadowForm : 0);
 		}
 		else
 		{
 			a.defer = prepare_defer_queue<ST, ALGO>(s);
-			if (s->statsEnabled) render_kernel<ST, ALGO, true, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			else render_kernel<ST, ALGO, false, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			if (s->statsEnabled) render_kernel<ST, ALGO, true, 1><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else render_kernel<ST, ALGO, false, 1><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			launch_shadow<ST, ALGO>(s, a, a.rgb, nullptr, s->shadowForm >= 0 ? s->shadowForm : 1);
 			launch_resume<ST, ALGO>(s, a);
 		}
@@ -1042,7 +1068,7 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 		a.defer = prepare_defer_queue<ST, ALGO>(s);
 		if (s->statsEnabled) trace_kernel<ST, ALGO, true, true><<<grid, 256, 0, s->stream>>>(a);
 		else trace_kernel<ST, ALGO, false, true><<<grid, 256, 0, s->stream>>>(a);
-		launch_shadow<ST, ALGO>(s, a, nullptr, colour, s->shadowForm >= 0 ? s->shadowForm : 1);
+		launch_shadow<ST, ALGO>(s, a, nullptr, colour, s->shadowForm >= 0 ? s->shadowForm : 2);  // incoherent rays: lane-level refill measured best (config 5: 12.2 vs 13.4 / 14.5 ms)
 		launch_resume<ST, ALGO>(s, a);
 	}
 	else
@@ -1087,11 +1113,44 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	if (chunkViews > ((1ull << 32) - 1) / a.viewPixels) chunkViews = ((1ull << 32) - 1) / a.viewPixels;
 	if (chunkViews < 1) chunkViews = 1;
 	const bool hash = s->storage == VRM_STORAGE_HASHTABLE, orig = algorithm == VRM_ALGO_ORIGINAL;
+	// The shadow-ray queue pipelines (modes 1, 4) touch the frame twice -- the render kernel's coalesced rows, then shadow_kernel's
+	// scattered black pixels -- which is fine in local memory but slow through PCIe / NVLink.  A frame that lives in page-locked host
+	// memory or on a peer GPU is therefore rendered into a local frame first and sent in one copy behind the kernels.  (The fused form,
+	// mode 2, stores every pixel once and writes remote frames directly while it computes.)
+	const int mode = s->renderMode >= 0 ? s->renderMode : ((!hash && !orig) ? 2 : 1);
+	bool viaLocal = false;
+	if ((mode == 1 || mode == 4) && s->light.useShadows)
+	{
+		cudaPointerAttributes at;
+		const bool local = cudaPointerGetAttributes(&at, d_rgb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == s->device;
+		cudaGetLastError();
+		viaLocal = !local;
+	}
+	const size_t frameBytes = (size_t)W * H * 3;
+	if (viaLocal)
+	{
+		const size_t need = (size_t)(chunkViews < nViews ? chunkViews : nViews) * frameBytes;
+		if (s->localFrameBytes < need)
+		{
+			VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+			if (s->d_localFrame) cudaFree(s->d_localFrame);
+			s->d_localFrame = nullptr; s->localFrameBytes = 0;
+			VRM_CUDA(s, cudaMalloc(&s->d_localFrame, need));
+			s->localFrameBytes = need;
+		}
+	}
 	for (uint64_t v0 = 0; v0 < nViews; v0 += chunkViews)
 	{
 		const uint32_t nv = (uint32_t)(nViews - v0 < chunkViews ? nViews - v0 : chunkViews);
 		a.cams = d_cams + v0 * 15;
 		a.rgb = d_rgb + v0 * a.viewPixels * 3;
+		a.rgbViewPixels = a.viewPixels;
+		if (viaLocal)
+		{
+			a.rgb = s->d_localFrame;
+			a.rgbViewPixels = (size_t)W * H;
+			a.rowWordsOk = ((W * 3u) % 4u == 0 && (frameBytes % 4 == 0 || nv == 1)) ? 1u : 0u;
+		}
 		a.hits = d_hits ? d_hits + v0 * a.viewPixels * 4 : nullptr;
 		a.nViews = nv;
 		dim3 grid((W + kBlockW - 1) / kBlockW, (yEnd - yBase + kBlockH - 1) / kBlockH, nv);
@@ -1100,6 +1159,13 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 		else if (orig) launch_render_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
 		else launch_render_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
 		VRM_CUDA(s, cudaGetLastError());
+		if (viaLocal)
+		{
+			const size_t rowBytes = (size_t)W * 3;
+			for (uint32_t v = 0; v < nv; v++)
+				VRM_CUDA(s, cudaMemcpyAsync(d_rgb + (v0 + v) * a.viewPixels * 3 + yBase * rowBytes, s->d_localFrame + v * frameBytes + yBase * rowBytes,
+				                            (size_t)(yEnd - yBase) * rowBytes, cudaMemcpyDefault, s->stream));
+		}
 	}
 	if (yEnd == H) vrm_signal_completion(s, nViews);  // (a band launch signals with the frame's last band)
 	return VRM_OK;
