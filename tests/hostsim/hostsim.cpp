@@ -49,7 +49,7 @@ struct SimScene
 
 Lighting gLight = {{0.57735026f, 0.57735026f, 0.57735026f}, {1, 1, 1}, {10, 10, -10}, 0, 1};
 unsigned long long gCrawlSkipped = 0;  // cluster-skip iterations fast-forwarded by crawl_skip (render calls only)
-int gFlat = 1;  // 1: the flat state machine of vrm_flat.cuh; 0: the nested form of vrm_core.cuh; 2: the lean machine of vrm_lean.cuh (what the hot render kernels run)
+int gFlat = 1;  // 1: the flat state machine of vrm_flat.cuh; 0: the nested form of vrm_core.cuh; 2: the lean machine of vrm_lean.cuh; 3: the flat machine with its fast paths (vrm_flat.cuh fast_jump / fast_nullskip) taken per ray
 unsigned long long gLeanParked = 0;  // rays the lean machine handed to the generic one (mode 2)
 
 template <int ST, int ALGO>
@@ -65,6 +65,7 @@ uint32_t march(RayCtx<ST, true>& c, const float* o, const float* d, float scale)
 		gLeanParked++;
 		c.reset();
 	}
+	if (gFlat == 3) return march_scene_flat_fast<ST, ALGO, true>(c, o, d, scale);  // the generic machine with its warp-uniform fast paths taken per ray
 	return gFlat ? march_scene_flat<ST, ALGO, true>(c, o, d, scale) : march_scene<ST, ALGO, true>(c, o, d, scale);
 }
 
@@ -452,5 +453,135 @@ extern "C" int sim_debug_ray(void* h, const float* ray, int algorithm, long from
 	};
 	if (algorithm == kAlgoOriginal) { FlatRay<kStorageVcs, kAlgoOriginal, true> r; run(r); }
 	else { FlatRay<kStorageVcs, kAlgoLongestAxis, true> r; run(r); }
+	return 0;
+}
+
+// ---- development aid (tools/warp_profile.py): what does a WARP of the render kernel execute? -----------------------------------
+// A fast VCS-only builder for full-size scenes (the std::map builder above is for the small test scenes) and a lockstep simulation of
+// march_scene_flat_warp over 8x4 pixel tiles that records, per pass, which blocks of the state machine have at least one lane.
+extern "C" int sim_scene_build_vcs_fast(void* h)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage != -1) return 1;
+	const size_t n = s->rgb.size();
+	for (size_t i = 0; i < 3 * n; i++) { const int r = floordiv64(s->xyz[i]); s->minCoord = std::min(s->minCoord, r); s->maxCoord = std::max(s->maxCoord, r); }
+	s->diameter = (uint32_t)(s->maxCoord - s->minCoord + 1);
+	const uint32_t D = s->diameter;
+	std::vector<std::pair<uint64_t, uint32_t>> keyed(n);  // (region z,y,x | cluster-major code, insertion index)
+	for (size_t i = 0; i < n; i++)
+	{
+		uint32_t u[3], l[3];
+		for (int a = 0; a < 3; a++) { const int v = s->xyz[3 * i + a], r = floordiv64(v); u[a] = (uint32_t)(r - s->minCoord); l[a] = (uint32_t)(v - r * 64); }
+		const uint32_t cid = ((l[0] >> 3) << 6) | ((l[1] >> 3) << 3) | (l[2] >> 3), code = ((l[0] & 7) << 6) | ((l[1] & 7) << 3) | (l[2] & 7);
+		keyed[i] = {((uint64_t)(u[0] + u[1] * D + u[2] * D * D) << 18) | (cid << 9) | code, (uint32_t)i};
+	}
+	std::sort(keyed.begin(), keyed.end());
+	s->regionTable.assign((size_t)D * D * D, -1);
+	int32_t ri = -1;
+	uint64_t lastRegion = ~0ull;
+	for (size_t i = 0; i < n; i++)
+	{
+		if (i + 1 < n && keyed[i + 1].first == keyed[i].first) continue;  // last write wins
+		const uint64_t region = keyed[i].first >> 18;
+		if (region != lastRegion)
+		{
+			lastRegion = region; ri++;
+			s->regionTable[(size_t)region] = ri;
+			s->headers.resize((size_t)(ri + 1) * 512 * 16, uint2{0, 0});
+			s->clusterMask.resize((size_t)(ri + 1) * 16, 0u);
+		}
+		const uint32_t cc = (uint32_t)(keyed[i].first & 0x3FFFFu), cid = cc >> 9;
+		uint2& w = s->headers[(size_t)ri * 8192 + (cc >> 5)];
+		if (w.x == 0u) w.y = (uint32_t)s->values.size();
+		w.x |= 1u << (cc & 31u);
+		s->clusterMask[(size_t)ri * 16 + (cid >> 5)] |= 1u << (cid & 31u);
+		s->values.push_back(s->rgb[keyed[i].second]);
+	}
+	s->filled = (uint32_t)(ri + 1);
+	for (uint32_t r = 0; r < s->filled; r++)
+		for (uint32_t w = 0; w < 8192; w++)
+			if ((s->clusterMask[(size_t)r * 16 + (w >> 9)] >> ((w >> 4) & 31)) & 1u) s->headers[(size_t)r * 8192 + w].y |= kHeaderClusterExists;
+	s->headers.resize(s->headers.size() + 80 * 16, uint2{0, 0});
+	s->clusterMask.resize(s->clusterMask.size() + 32, 0u);
+	s->storage = kStorageVcs;
+	return 0;
+}
+
+// Categories a lane can be in at the top of a pass: 0 region (stored, or leaving the scene), 1 head, 2 main/test, 3 main/jump, 4 main/next, 5 main/cluster, 6 region (null: skip),
+// 7 waiting with a hit, 8 done.  hist[signature] += 1 per pass, signature = bit mask of the categories present; lanes[signature][category] += lanes.
+// Tiles (8x4 pixels) are sampled every tileStride-th in both directions.  VCS + longest axis only.
+extern "C" int sim_warp_profile(void* h, const float* cam, const float* tr, uint32_t scale, uint32_t W, uint32_t H, uint32_t tileStride,
+	uint64_t* hist /*512*/, uint64_t* lanes /*512*9*/, uint64_t* totals /*4: tiles, passes, shade passes, lane-passes marching*/, int nThreads)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage != kStorageVcs) return 1;
+	using Ray = FlatRay<kStorageVcs, kAlgoLongestAxis, false>;
+	const uint32_t tilesX = (W + 7) / 8, tilesY = (H + 3) / 4;
+	std::vector<uint64_t> H0(512, 0), L0(512 * 9, 0);
+	uint64_t T[4] = {0, 0, 0, 0};
+	#pragma omp parallel num_threads(nThreads)
+	{
+		std::vector<uint64_t> hl(512, 0), ll(512 * 9, 0);
+		uint64_t t[4] = {0, 0, 0, 0};
+		RayCtx<kStorageVcs, false> c;
+		c.sv = s->view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = nullptr;
+		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
+		c.reset();
+		c.skipDead = 1u;
+		#pragma omp for schedule(dynamic, 1)
+		for (int64_t ty = 0; ty < (int64_t)tilesY; ty += tileStride)
+			for (uint32_t tx = 0; tx < tilesX; tx += tileStride)
+			{
+				Ray ray[32];
+				for (int l = 0; l < 32; l++)
+				{
+					const uint32_t x = tx * 8 + (l & 7), y = (uint32_t)ty * 4 + (l >> 3);
+					ray[l].st = kStDone; ray[l].result = 0; ray[l].mode = 0;
+					if (x < W && y < H)
+					{
+						float o[3], d[3];
+						primary_ray_flat(cam, x, y, W, H, 1.0f / (float)W, 1.0f / (float)H, o, d);
+						ray[l].start_primary(c, o, d, (float)scale);
+					}
+				}
+				t[0]++;
+				for (;;)
+				{
+					uint32_t sig = 0; int cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+					bool marching = false, anyHit = false;
+					for (int l = 0; l < 32; l++)
+					{
+						int cat;
+						switch (ray[l].st)
+						{
+						case kStRegion: cat = ray[l].ri == -1 ? 6 : 0; break;
+						case kStHead: cat = 1; break;
+						case kStMain: cat = ray[l].mode == kAdvNone ? 2 : (ray[l].mode == kAdvJump ? 3 : (ray[l].mode == kAdvNext ? 4 : (ray[l].mode == kAdvCluster ? 5 : 6))); break;
+						case kStHit: cat = 7; anyHit = true; break;
+						default: cat = 8; break;
+						}
+						if (cat <= 6) marching = true;
+						sig |= 1u << cat; cnt[cat]++;
+					}
+					if (marching)
+					{
+						hl[sig]++; t[1]++;
+						for (int k = 0; k < 9; k++) ll[sig * 9 + k] += cnt[k];
+						for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) { ray[l].template step_marching<kPpOff>(c); t[3]++; }
+						continue;
+					}
+					if (!anyHit) break;
+					t[2]++;
+					for (int l = 0; l < 32; l++) if (ray[l].st == kStHit) ray[l].do_hit(c);
+				}
+			}
+		#pragma omp critical
+		{
+			for (int i = 0; i < 512; i++) H0[i] += hl[i];
+			for (int i = 0; i < 512 * 9; i++) L0[i] += ll[i];
+			for (int i = 0; i < 4; i++) T[i] += t[i];
+		}
+	}
+	memcpy(hist, H0.data(), 512 * 8); memcpy(lanes, L0.data(), 512 * 9 * 8); memcpy(totals, T, 32);
 	return 0;
 }

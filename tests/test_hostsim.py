@@ -7,7 +7,7 @@ import pytest
 from tests.common import COMBOS, MINI_CAMERAS, PROBE_CAMERAS, build_oracle, camera, lookup_queries, oracle_kind, po, scenes
 
 
-FORMS = {"nested": 0, "flat": 1, "lean": 2}
+FORMS = {"nested": 0, "flat": 1, "lean": 2, "fast": 3}
 
 
 @pytest.fixture(params=list(FORMS), autouse=True)

@@ -381,12 +381,16 @@ template <int ST, bool STATS> struct RayCtx
 	int32_t hit[4];
 	// Queue of rays handed to the resume kernel (vrm_flat.cuh kPpDefer, vrm_render.cu resume_kernel); null = none
 	void* deferQueue;
+	// 1: a hit whose shaded colour is already black starts no shadow ray (Renderer.cuh:314-315: 0 * !isInShadow = 0 whatever the shadow
+	// ray finds).  0 (host harness, reference-comparable event counters): every hit's shadow ray is traced, as the reference does.
+	uint32_t skipDead;
 	Stats st;
 
 	VRM_HD void reset()
 	{
 		hit[0] = hit[1] = hit[2] = hit[3] = 0;
 		deferQueue = nullptr;
+		skipDead = 0u;
 		if (STATS) { st.nExist = st.nExistFalse = st.nLookup = st.nLookupHit = st.nProbe2 = st.nRegionReads = st.nCrawlSkipped = 0; }
 	}
 };

@@ -88,6 +88,9 @@ constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
 #ifndef VRM_PP_DEFAULT
 #define VRM_PP_DEFAULT 2
 #endif
+#ifndef VRM_FAST_PATHS
+#define VRM_FAST_PATHS 1   // march_scene_flat_warp (VCS + longest axis): warp-uniform fast paths for all-jump / all-null-region passes (FlatRay::fast_jump)
+#endif
 constexpr int kPpDefault = VRM_PP_DEFAULT;  // single-ray callers (host harness; 0 there = crawl like the reference); the kernels name their policy
 
 struct DeferHeader
@@ -350,7 +353,7 @@ struct FlatRay
 	{
 		ShadowStart ss;
 		shade_hit(c, ss);
-		if (!c.light.useShadows) { finish(ss.lit); return; }
+		if (!c.light.useShadows || (c.skipDead && ss.lit == 0u)) { finish(ss.lit); return; }
 		start_shadow(c, ss);
 	}
 
@@ -461,6 +464,78 @@ struct FlatRay
 		}
 	}
 
+	// A voxel was found right after an advance (the voxel under the new position).  Original algorithm: Renderer.cuh:312-315; jump:
+	// Renderer.cuh:733-738 (tMin carries +EPSILON there, so the comparison normally falls through to the Z normal).
+	// getNormalFromTValues tests X, then Y, else Z.
+	VRM_HD void hit_after_advance(RayCtx<ST, STATS>& c, uint32_t col, bool jump)
+	{
+		const PermRuntime p = unpack_perm(fl);
+		int mW = 0;
+		if (fl & kFlEq0) mW |= 1 << p.a0;
+		if (fl & (kFlEq0 << 1)) mW |= 1 << p.a1;
+		if (fl & (kFlEq0 << 2)) mW |= 1 << p.a2;
+		const int nAxisW = (mW & 1) ? 0 : ((mW & 2) ? 1 : 2);
+		const float dn = p.a0 == nAxisW ? d[0] : (p.a1 == nAxisW ? d[1] : d[2]);  // scaled direction = s * d, s > 0: same sign
+		record_hit(c, col, o[0], o[1], o[2], nAxisW, copysignf(1.0f, -dn), jump, g[0], g[1], g[2]);
+	}
+
+	// the jump reached a cluster that exists but the voxel is empty: re-snap to the longest axis and `continue` the while loop
+	// (Renderer.cuh:742-750)
+	VRM_HD void resnap_after_jump()
+	{
+		const float tNext = div1(vsub(sd[0] > 0.0f ? ceilf(o[0]) : floorf(o[0]), o[0]), sd[0], srd[0], thr);
+		const float tt = vadd(tNext, kEps);
+		ro[0] = along(o[0], tt, sd[0]); ro[1] = along(o[1], tt, sd[1]); ro[2] = along(o[2], tt, sd[2]);
+		ad1 = (int)ro[1] - g[1];
+		ad2 = (int)ro[2] - g[2];
+		st = kStHead;
+	}
+
+	// ---- WARP-UNIFORM FAST PATHS (VCS + longest axis) ----------------------------------------------------------------------
+	// The generic kStMain block serves five advance modes with selects and branches; a lockstep simulation of the bench frame
+	// (tools/warp_profile.py) shows that in 27 % of a warp's passes EVERY marching lane is in a cluster jump and in ~20 % every
+	// marching lane stands at the entry of a null region.  For those passes the warp runs one of the two blocks below: do_main with
+	// the mode constant-folded -- the same operations on the same values in the same order, nothing else.  A lane whose step needs
+	// anything outside the common case (IEEE slow-path division: unsafe direction, denormal-range or ZERO numerator -- which is
+	// also the only way into the crawl fast-forwards, since m == 0 needs a zero numerator) returns false WITHOUT having changed
+	// anything; the caller then runs the generic pass for the warp.
+	//
+	// do_main with mode == kAdvJump: one iteration of performVoxelSpaceJump's loop (Renderer.cuh:707-750)
+	VRM_HD bool fast_jump(RayCtx<ST, STATS>& c)
+	{
+		const float n0 = vadd((float)(int)((uint32_t)g[0] & ~7u), sd[0] > 0.0f ? 8.0f : 0.0f);
+		const float n1 = vadd((float)(int)((uint32_t)g[1] & ~7u), sd[1] > 0.0f ? 8.0f : 0.0f);
+		const float n2 = vadd((float)(int)((uint32_t)g[2] & ~7u), sd[2] > 0.0f ? 8.0f : 0.0f);
+		const float x0 = vsub(n0, o[0]), x1 = vsub(n1, o[1]), x2 = vsub(n2, o[2]);
+		if (!(fminf(fabsf(x0), fminf(fabsf(x1), fabsf(x2))) >= thr)) return false;  // div3's slow path (also every m == 0 case)
+		const float a0 = div_by_const(x0, sd[0], srd[0]), a1 = div_by_const(x1, sd[1], srd[1]), a2 = div_by_const(x2, sd[2], srd[2]);
+		const float s = vadd(min3(a0, a1, a2), kEps);  // the jump guards nothing (Renderer.cuh:457-459) and its tMin includes +EPSILON (713-716)
+		fl = (fl & ~kFlEqMask) | (a0 == s ? kFlEq0 : 0u) | (a1 == s ? kFlEq0 << 1 : 0u) | (a2 == s ? kFlEq0 << 2 : 0u);
+		o[0] = along(o[0], s, sd[0]); o[1] = along(o[1], s, sd[1]); o[2] = along(o[2], s, sd[2]);
+		if (!ray_in_region(o)) { change_region(c); return true; }
+		g[0] = (int)o[0]; g[1] = (int)o[1]; g[2] = (int)o[2];
+		uint32_t col;
+		const bool e = voxel_test(c, g[0], g[1], g[2], col);
+		if (col != kEmpty) hit_after_advance(c, col, true);
+		else if (e) resnap_after_jump();
+		return true;
+	}
+
+	// do_region with ri == -1 followed by do_main with mode == kAdvRegion: skip to the null region's edge, no +EPSILON
+	// (Renderer.cuh:384-410, guarded twin 185-211 -- with a finite thr no direction component is zero, so the guards are moot)
+	VRM_HD bool fast_nullskip(RayCtx<ST, STATS>& c)
+	{
+		const float lo = vsub(0.0f, kEps), hi = vadd((float)kRegion, kEps);
+		const float x0 = vsub(d[0] > 0.0f ? hi : lo, o[0]), x1 = vsub(d[1] > 0.0f ? hi : lo, o[1]), x2 = vsub(d[2] > 0.0f ? hi : lo, o[2]);  // 0.0f + lo = lo, 0.0f + hi = hi
+		if (!(fminf(fabsf(x0), fminf(fabsf(x1), fabsf(x2))) >= thr)) return false;
+		const float a0 = div_by_const(x0, d[0], rd[0]), a1 = div_by_const(x1, d[1], rd[1]), a2 = div_by_const(x2, d[2], rd[2]);
+		const float s = min3(a0, a1, a2);
+		mode = kAdvRegion;
+		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
+		change_region(c);
+		return true;
+	}
+
 	// ---- kStMain: [one advance] + one voxel test ------------------------------------------------------------------------
 	// NOSKIP: plain execution without the crawl / ping-pong fast-forwards (the fast-forwards use it to probe cycles)
 	template <bool NOSKIP = false, int PP = kPpDefault>
@@ -546,19 +621,7 @@ struct FlatRay
 
 		if (col != kEmpty)
 		{
-			if (!test)
-			{
-				// original algorithm: Renderer.cuh:312-315; jump: Renderer.cuh:733-738 (tMin carries +EPSILON there, so the
-				// comparison normally falls through to the Z normal).  getNormalFromTValues tests X, then Y, else Z.
-				const PermRuntime p = unpack_perm(fl);
-				int mW = 0;
-				if (fl & kFlEq0) mW |= 1 << p.a0;
-				if (fl & (kFlEq0 << 1)) mW |= 1 << p.a1;
-				if (fl & (kFlEq0 << 2)) mW |= 1 << p.a2;
-				const int nAxisW = (mW & 1) ? 0 : ((mW & 2) ? 1 : 2);
-				const float dn = p.a0 == nAxisW ? d[0] : (p.a1 == nAxisW ? d[1] : d[2]);  // scaled direction = s * d, s > 0: same sign
-				record_hit(c, col, o[0], o[1], o[2], nAxisW, copysignf(1.0f, -dn), jump, g[0], g[1], g[2]);
-			}
+			if (!test) hit_after_advance(c, col, jump);
 			else if constexpr (kLA)
 			{
 				const PermRuntime p = unpack_perm(fl);
@@ -582,17 +645,7 @@ struct FlatRay
 			if (!jump) mode = e ? kAdvNext : kAdvCluster;
 			else if (e)
 			{
-				if constexpr (kLA)
-				{
-					// the jump reached a cluster that exists but the voxel is empty: re-snap to the longest axis and `continue`
-					// the while loop (Renderer.cuh:742-750)
-					const float tNext = div1(vsub(sd[0] > 0.0f ? ceilf(o[0]) : floorf(o[0]), o[0]), sd[0], srd[0], thr);
-					const float tt = vadd(tNext, kEps);
-					ro[0] = along(o[0], tt, sd[0]); ro[1] = along(o[1], tt, sd[1]); ro[2] = along(o[2], tt, sd[2]);
-					ad1 = (int)ro[1] - g[1];
-					ad2 = (int)ro[2] - g[2];
-					st = kStHead;
-				}
+				if constexpr (kLA) resnap_after_jump();
 			}
 			// else: still no voxel space: another jump iteration (mode stays kAdvJump)
 			return;
@@ -793,6 +846,19 @@ struct FlatRay
 		return st == kStDone;
 	}
 
+	// step() with the warp-uniform fast paths taken per ray whenever they apply: what a warp whose lanes all qualify executes
+	// (host harness: the CPU tier checks the fast paths against the oracle this way, tests/test_hostsim.py form "fast")
+	template <int PP = kPpDefault>
+	VRM_HD bool step_fast(RayCtx<ST, STATS>& c)
+	{
+		if constexpr (kLA && ST == kStorageVcs)
+		{
+			if (st == kStMain && mode == kAdvJump) { if (fast_jump(c)) return st == kStDone; }
+			else if (st == kStRegion && ri == -1) { if (fast_nullskip(c)) return st == kStDone; }
+		}
+		return step<PP>(c);
+	}
+
 	// the marching blocks only (region -> head -> main); hits are shaded by the caller
 	template <int PP = kPpDefault>
 	VRM_HD void step_marching(RayCtx<ST, STATS>& c)
@@ -841,6 +907,43 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 	ray.st = kStDone; ray.result = 0;
 	if (active) ray.start_primary(c, originW, dirW, scale);
 #if defined(__CUDA_ARCH__)
+#if VRM_FAST_PATHS
+	if constexpr (ALGO != kAlgoOriginal && ST == kStorageVcs)
+	{
+		bool generic = false;  // warp-uniform: a lane's step did not qualify for the fast path it was offered
+		for (;;)
+		{
+			// what the warp's marching lanes (kStMain, kStRegion, kStHead) are about to do: 1 a cluster jump, 2 a null-region skip, 4 anything else
+			const bool isJump = ray.st == kStMain && ray.mode == kAdvJump, isNull = ray.st == kStRegion && ray.ri == -1;
+			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : 4u)) : 0u;
+			const unsigned all = __reduce_or_sync(0xFFFFFFFFu, cls);
+			if (all == 0u)
+			{
+				// nobody is marching: every lane is waiting with a hit, done or parked
+				if (!__any_sync(0xFFFFFFFFu, ray.st == kStHit)) break;
+				if (ray.st == kStHit) ray.do_hit(c);
+				continue;
+			}
+			if (!generic && all == 1u)
+			{
+				bool ok = true;
+				if (isJump) ok = ray.fast_jump(c);
+				generic = __any_sync(0xFFFFFFFFu, !ok);
+				continue;
+			}
+			if (!generic && all == 2u)
+			{
+				bool ok = true;
+				if (isNull) ok = ray.fast_nullskip(c);
+				generic = __any_sync(0xFFFFFFFFu, !ok);
+				continue;
+			}
+			warp_march_pass<ST, ALGO, STATS, PP>(c, ray);
+			generic = false;
+		}
+	}
+	else
+#endif
 	for (;;)
 	{
 		const unsigned marching = __ballot_sync(0xFFFFFFFFu, ray.st <= kStHead);  // kStMain, kStRegion, kStHead
@@ -922,6 +1025,16 @@ VRM_HD uint32_t march_scene_flat(RayCtx<ST, STATS>& c, const float* originW, con
 {
 	int unused;
 	return march_scene_flat<ST, ALGO, STATS, kPpDefault>(c, originW, dirW, scale, unused);
+}
+
+// The same with the fast paths taken whenever a ray qualifies (host harness)
+template <int ST, int ALGO, bool STATS>
+VRM_HD uint32_t march_scene_flat_fast(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
+{
+	FlatRay<ST, ALGO, STATS> ray;
+	ray.start_primary(c, originW, dirW, scale);
+	while (ray.st < kStDone) ray.template step_fast<kPpDefault>(c);
+	return ray.result;
 }
 
 }  // namespace vrm

@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kRenderThreads, ((FORM != 0 && ALGO != kAlgoOr
 		c.deferQueue = a.defer;
 		if constexpr (FORM == 2)
 		{
+			c.skipDead = a.skipDead;
 			// both phases here: lanes that hit wait at the hit barrier, the tile then shades and walks its shadow rays together
 			int slot;
 			color = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, slot);
@@ -1006,6 +1007,7 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 	if (mode == 2)  // state machine, both phases in one kernel (hit barrier) + the rays it parked
 	{
 		a.defer = prepare_defer_queue<ST, ALGO>(s);
+		a.skipDead = s->statsMode == 1 ? 0u : 1u;  // as in prepare_shadow_queue
 		if (s->statsEnabled) render_kernel<ST, ALGO, true, 2><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		else render_kernel<ST, ALGO, false, 2><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		launch_resume<ST, ALGO>(s, a);
