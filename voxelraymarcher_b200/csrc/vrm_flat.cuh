@@ -88,6 +88,9 @@ constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
 #ifndef VRM_PP_DEFAULT
 #define VRM_PP_DEFAULT 2
 #endif
+#ifndef VRM_FAST_LOOPS
+#define VRM_FAST_LOOPS 1   // the warp stays inside a fast block while every marching lane still qualifies
+#endif
 #ifndef VRM_FAST_PATHS
 #define VRM_FAST_PATHS 1   // march_scene_flat_warp (VCS + longest axis): warp-uniform fast paths for all-jump / all-null-region passes (FlatRay::fast_jump)
 #endif
@@ -924,6 +927,35 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				if (ray.st == kStHit) ray.do_hit(c);
 				continue;
 			}
+#if VRM_FAST_LOOPS
+			// The warp stays in a fast block for as long as every marching lane still qualifies (two votes per pass instead of the
+			// classification above): fast_jump leaves a lane in kStMain / kAdvJump, or in kStRegion / kStHead / kStHit; fast_nullskip
+			// leaves it in kStRegion.
+			if (!generic && all == 1u)
+			{
+				for (;;)
+				{
+					bool ok = true;
+					if (ray.st == kStMain) ok = ray.fast_jump(c);
+					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kStMain);
+					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || ray.st == kStRegion || ray.st == kStHead);
+					if (leave != 0u || stay == 0u) { generic = __any_sync(0xFFFFFFFFu, !ok); break; }
+				}
+				continue;
+			}
+			if (!generic && all == 2u)
+			{
+				for (;;)
+				{
+					bool ok = true;
+					if (ray.st == kStRegion) ok = ray.fast_nullskip(c);
+					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kStRegion && ray.ri == -1);
+					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || (ray.st == kStRegion && ray.ri != -1));
+					if (leave != 0u || stay == 0u) { generic = __any_sync(0xFFFFFFFFu, !ok); break; }
+				}
+				continue;
+			}
+#else
 			if (!generic && all == 1u)
 			{
 				bool ok = true;
@@ -938,6 +970,7 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				generic = __any_sync(0xFFFFFFFFu, !ok);
 				continue;
 			}
+#endif
 			warp_march_pass<ST, ALGO, STATS, PP>(c, ray);
 			generic = false;
 		}

@@ -32,12 +32,19 @@ namespace
 #define VRM_TRACE_HIT_BARRIER 0  // the same for trace_rays (arbitrary rays)
 #endif
 #ifndef VRM_WARP_STORE
-#define VRM_WARP_STORE 0
+#define VRM_WARP_STORE 1        // fused form (VCS + longest axis): per-warp stores when the frame is in this GPU's memory (1.398 -> 1.377 ms; with 9 CTAs per SM 1.363)
+#endif
+#ifndef VRM_WARP_STORE_QUEUE
+#define VRM_WARP_STORE_QUEUE 0  // the same for the nested-loop render kernels of the shadow-ray queue pipelines
 #endif
 #ifndef VRM_FLAT_LA_MINBLOCKS
 #define VRM_FLAT_LA_MINBLOCKS 4
 #endif
 
+#ifndef VRM_FUSED_CTAS
+#define VRM_FUSED_CTAS 9   // > 0: resident CTAs per SM the fused form (FORM 2) is compiled for, 0: VRM_FLAT_LA_MINBLOCKS * 2.  Measured with the fast paths in
+                           // place: 7 (72 registers, no spills) 1.439 ms, 8 (64) 1.398, 9 (56, ~0.5 KB of spills) 1.379, 10 (48) 1.404 -- occupancy beats the spills up to 36 warps
+#endif
 #ifndef VRM_TILE_W
 #define VRM_TILE_W 8
 #endif
@@ -59,6 +66,7 @@ struct RenderArgs
 	size_t viewPixels;     // pixel slots between the outputs of consecutive views (W * H, or a multiple of it for interleaved view sharding)
 	size_t rgbViewPixels;  // the same for the frame array `rgb` alone (it differs when the frames are rendered into the handle's local buffer first)
 	float invW, invH;      // RN(1 / W), RN(1 / H) (host): exact division by a constant in primary_ray_flat
+	uint32_t rgbLocal;     // host side only: the frame `rgb` points into this GPU's own memory (selects the per-warp store kernels)
 	uint32_t rowWordsOk;   // 1 when every 32-pixel row segment starts on a 4-byte boundary (W * 3 % 4 == 0 and an aligned base)
 	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
 	uint8_t* rgb;       // nViews x H x W x 3
@@ -199,8 +207,12 @@ __global__ void __launch_bounds__(kResumeThreads) resume_kernel(const ResumeArgs
 
 // FORM 0: nested loops, primary rays only (shadow rays go to the queue); 1: state machine, primary rays only; 2: state machine with the
 // shadow ray in the kernel behind a hit barrier (march_scene_flat_warp) -- the default for VCS + longest axis, see launch_render_t
-template <int ST, int ALGO, bool STATS, int FORM>
-__global__ void __launch_bounds__(kRenderThreads, ((FORM != 0 && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? (ALGO == kAlgoOriginal ? 6 : 5) : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
+// WSTORE: every warp writes its own 8x4 tile (four 24-byte row segments) and leaves -- no CTA barrier, so a warp that finishes early does
+// not wait for the slowest tile of its CTA (14 % of the warp-samples of the fused kernel sat at that barrier, profiles/r02g).  Chosen
+// when the frame lives in this GPU's memory; frames in page-locked host memory or on a peer GPU keep the CTA-staged 96-byte rows
+// (fewer, larger transactions over PCIe / NVLink).
+template <int ST, int ALGO, bool STATS, int FORM, bool WSTORE>
+__global__ void __launch_bounds__(kRenderThreads, (FORM == 2 && VRM_FUSED_CTAS > 0) ? VRM_FUSED_CTAS : ((FORM != 0 && ALGO != kAlgoOriginal) ? VRM_FLAT_LA_MINBLOCKS : (ST == kStorageHash ? (ALGO == kAlgoOriginal ? 6 : 5) : (ALGO == kAlgoOriginal ? 6 : 4))) * 8 / (VRM_BLOCK_TILES_Y * VRM_BLOCK_TILES_X)) render_kernel(const RenderArgs a)
 {
 	constexpr bool FLATLOOP = FORM != 0;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -287,7 +299,8 @@ __global__ void __launch_bounds__(kRenderThreads, ((FORM != 0 && ALGO != kAlgoOr
 	// the shadow ray of a hit goes to the queue; without shadows (USE_SHADOWS false, Main.cu:41) the shaded colour is final
 	if constexpr (FORM != 2) { if (a.shadowItems) shadow_enqueue(a, hit, ss, (uint32_t)pixelOut); }
 	// writeColorToFramebuffer, Renderer.cuh:1024-1031 (red = colour >> 16, unmasked, then narrowed to a byte)
-#if VRM_WARP_STORE
+	if constexpr (WSTORE)
+	{
 	// per-warp staging: each warp writes its own 8x4 tile as four 24-byte row segments, no CTA barrier
 	const uint32_t tx0 = x0 + (warp % kBlockTilesX) * kTileW, ty0 = y0 + (warp / kBlockTilesX) * kTileH;
 	const bool wholeTile = tx0 + kTileW <= a.W && ty0 + kTileH <= a.yEnd && a.rowWordsOk;
@@ -304,7 +317,16 @@ __global__ void __launch_bounds__(kRenderThreads, ((FORM != 0 && ALGO != kAlgoOr
 			dst[w] = mine[row][w];
 		}
 	}
-#else
+	else if (inside)
+	{
+		const size_t p = pixelOut;
+		a.rgb[3 * p] = (uint8_t)(color >> 16);
+		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
+		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
+	}
+	}
+	else
+	{
 	const bool wholeBlock = x0 + kBlockW <= a.W && y0 + kBlockH <= a.yEnd && a.rowWordsOk;
 	if (wholeBlock)
 	{
@@ -318,13 +340,13 @@ __global__ void __launch_bounds__(kRenderThreads, ((FORM != 0 && ALGO != kAlgoOr
 			dst[w] = staged[row][w];
 		}
 	}
-#endif
 	else if (inside)
 	{
 		const size_t p = pixelOut;
 		a.rgb[3 * p] = (uint8_t)(color >> 16);
 		a.rgb[3 * p + 1] = (uint8_t)((color >> 8) & 0xFF);
 		a.rgb[3 * p + 2] = (uint8_t)(color & 0xFF);
+	}
 	}
 	flush_stats<STATS>(c, a.stats);
 }
@@ -1008,8 +1030,9 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 	{
 		a.defer = prepare_defer_queue<ST, ALGO>(s);
 		a.skipDead = s->statsMode == 1 ? 0u : 1u;  // as in prepare_shadow_queue
-		if (s->statsEnabled) render_kernel<ST, ALGO, true, 2><<<grid, kRenderThreads, 0, s->stream>>>(a);
-		else render_kernel<ST, ALGO, false, 2><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		if (s->statsEnabled) render_kernel<ST, ALGO, true, 2, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		else if (a.rgbLocal && VRM_WARP_STORE) render_kernel<ST, ALGO, false, 2, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+		else render_kernel<ST, ALGO, false, 2, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 		launch_resume<ST, ALGO>(s, a);
 		return;
 	}
@@ -1020,15 +1043,16 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 		if (prepare_shadow_queue(s, (size_t)grid.x * grid.y * grid.z * kRenderThreads, a) != VRM_OK) return;
 		if (mode == 1)
 		{
-			if (s->statsEnabled) render_kernel<ST, ALGO, true, 0><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			else render_kernel<ST, ALGO, false, 0><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			if (s->statsEnabled) render_kernel<ST, ALGO, true, 0, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else if (a.rgbLocal && VRM_WARP_STORE_QUEUE) render_kernel<ST, ALGO, false, 0, true><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else render_kernel<ST, ALGO, false, 0, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			launch_shadow<ST, ALGO>(s, a, a.rgb, nullptr, s->shadowForm >= 0 ? s->shadowForm : 0);
 		}
 		else
 		{
 			a.defer = prepare_defer_queue<ST, ALGO>(s);
-			if (s->statsEnabled) render_kernel<ST, ALGO, true, 1><<<grid, kRenderThreads, 0, s->stream>>>(a);
-			else render_kernel<ST, ALGO, false, 1><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			if (s->statsEnabled) render_kernel<ST, ALGO, true, 1, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
+			else render_kernel<ST, ALGO, false, 1, false><<<grid, kRenderThreads, 0, s->stream>>>(a);
 			launch_shadow<ST, ALGO>(s, a, a.rgb, nullptr, s->shadowForm >= 0 ? s->shadowForm : 1);
 			launch_resume<ST, ALGO>(s, a);
 		}
@@ -1121,12 +1145,12 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 	// mode 2, stores every pixel once and writes remote frames directly while it computes.)
 	const int mode = s->renderMode >= 0 ? s->renderMode : ((!hash && !orig) ? 2 : 1);
 	bool viaLocal = false;
-	if ((mode == 1 || mode == 4) && s->light.useShadows)
 	{
 		cudaPointerAttributes at;
 		const bool local = cudaPointerGetAttributes(&at, d_rgb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == s->device;
 		cudaGetLastError();
-		viaLocal = !local;
+		a.rgbLocal = local ? 1u : 0u;
+		viaLocal = !local && (mode == 1 || mode == 4) && s->light.useShadows;
 	}
 	const size_t frameBytes = (size_t)W * H * 3;
 	if (viaLocal)
@@ -1150,6 +1174,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 		if (viaLocal)
 		{
 			a.rgb = s->d_localFrame;
+			a.rgbLocal = 1u;
 			a.rgbViewPixels = (size_t)W * H;
 			a.rowWordsOk = ((W * 3u) % 4u == 0 && (frameBytes % 4 == 0 || nv == 1)) ? 1u : 0u;
 		}
