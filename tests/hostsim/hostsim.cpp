@@ -561,10 +561,14 @@ extern "C" int sim_warp_profile(void* h, const float* cam, const float* tr, uint
 						default: cat = 8; break;
 						}
 						if (cat <= 6) marching = true;
-						sig |= 1u << cat; cnt[cat]++;
+						if (cat < 8) sig |= 1u << cat;
+						cnt[cat]++;
 					}
 					if (marching)
 					{
+						bool shadowPass = false;
+						for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead && ray[l].shadow()) shadowPass = true;
+						if (shadowPass) sig |= 256u;  // (the hit barrier makes a pass all-primary or all-shadow; bit 8 = "done" is not a marching category)
 						hl[sig]++; t[1]++;
 						for (int k = 0; k < 9; k++) ll[sig * 9 + k] += cnt[k];
 						for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) { ray[l].template step_marching<kPpOff>(c); t[3]++; }

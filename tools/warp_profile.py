@@ -46,19 +46,21 @@ def main():
     tiles, passes, shade, lanepasses = (int(v) for v in tot)
     print(f"tiles {tiles}  passes/tile {passes / tiles:.2f}  shading passes/tile {shade / tiles:.2f}  marching lanes/pass {lanepasses / passes:.2f}")
     print("passes in which a category is present, lanes in it when present:")
-    for k, name in enumerate(CATS):
+    for k, name in enumerate(CATS[:8]):
         p = sum(int(hist[s]) for s in range(512) if (s >> k) & 1)
         l = sum(int(lanes[s, k]) for s in range(512))
         print(f"  {name:9s} {100 * p / passes:6.2f} % of passes, {l / max(p, 1):5.1f} lanes")
-    print("most frequent signatures (marching categories only):")
+    shadow = sum(int(hist[s]) for s in range(512) if s & 256)
+    print(f"shadow-ray passes {100 * shadow / passes:.1f} % of passes")
+    print("most frequent signatures (marching categories only; S = shadow-ray pass):")
     agg = {}
     for s in range(512):
         if hist[s]:
-            m = s & 0x7F
+            m = s & 0x17F
             e = agg.setdefault(m, [0, np.zeros(9)])
             e[0] += int(hist[s]); e[1] += lanes[s].astype(np.float64)
     for m, (n, l) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
-        names = "+".join(CATS[k] for k in range(7) if (m >> k) & 1)
+        names = ("S " if m & 256 else "P ") + "+".join(CATS[k] for k in range(7) if (m >> k) & 1)
         print(f"  {100 * n / passes:6.2f} %  {names:40s} " + " ".join(f"{CATS[k][:4]}={l[k] / n:.1f}" for k in range(9) if l[k]))
 
 

@@ -88,6 +88,9 @@ constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
 #ifndef VRM_PP_DEFAULT
 #define VRM_PP_DEFAULT 2
 #endif
+#ifndef VRM_FAST_LA
+#define VRM_FAST_LA 7      // a third warp-uniform block: longest-axis stepping (FlatRay::fast_la); A/B bits: 2 = without the stored-region entry, 4 = without the inner loop
+#endif
 #ifndef VRM_FAST_LOOPS
 #define VRM_FAST_LOOPS 1   // the warp stays inside a fast block while every marching lane still qualifies
 #endif
@@ -524,6 +527,16 @@ struct FlatRay
 		return true;
 	}
 
+	// Longest-axis stepping: every marching lane of the warp is entering a stored region, at the loop head, or has voxel tests of its
+	// iteration left (28 % of the passes of the bench frame).  The generic pass minus its advance half and its dispatch; a lane that
+	// leaves the pattern (empty cluster -> jump, leaving the region -> original algorithm's tail) just waits for the next pass.
+	VRM_HD void fast_la(RayCtx<ST, STATS>& c)
+	{
+		if ((VRM_FAST_LA & 2) == 0) { if (st == kStRegion) do_region(c); }  // (ri != -1: the caller keeps null regions for fast_nullskip)
+		if (st == kStHead) do_head();
+		if (st == kStMain && mode == kAdvNone) do_main<false, kPpOff, true>(c);
+	}
+
 	// do_region with ri == -1 followed by do_main with mode == kAdvRegion: skip to the null region's edge, no +EPSILON
 	// (Renderer.cuh:384-410, guarded twin 185-211 -- with a finite thr no direction component is zero, so the guards are moot)
 	VRM_HD bool fast_nullskip(RayCtx<ST, STATS>& c)
@@ -541,12 +554,13 @@ struct FlatRay
 
 	// ---- kStMain: [one advance] + one voxel test ------------------------------------------------------------------------
 	// NOSKIP: plain execution without the crawl / ping-pong fast-forwards (the fast-forwards use it to probe cycles)
-	template <bool NOSKIP = false, int PP = kPpDefault>
+	// TESTONLY: the caller guarantees mode == kAdvNone (fast_la): the advance half is compiled out
+	template <bool NOSKIP = false, int PP = kPpDefault, bool TESTONLY = false>
 	VRM_HD void do_main(RayCtx<ST, STATS>& c)
 	{
 		int slot = 0;
-		const bool test = kLA && mode == kAdvNone;
-		const bool jump = kLA && mode == kAdvJump;
+		const bool test = kLA && (TESTONLY || mode == kAdvNone);
+		const bool jump = kLA && !TESTONLY && mode == kAdvJump;
 		if (!test)
 		{
 			const bool skip = mode == kAdvRegion;
@@ -858,6 +872,7 @@ struct FlatRay
 		{
 			if (st == kStMain && mode == kAdvJump) { if (fast_jump(c)) return st == kStDone; }
 			else if (st == kStRegion && ri == -1) { if (fast_nullskip(c)) return st == kStDone; }
+			else if (st == kStHead || (st == kStMain && mode == kAdvNone) || st == kStRegion) { fast_la(c); return st == kStDone; }
 		}
 		return step<PP>(c);
 	}
@@ -918,7 +933,13 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 		{
 			// what the warp's marching lanes (kStMain, kStRegion, kStHead) are about to do: 1 a cluster jump, 2 a null-region skip, 4 anything else
 			const bool isJump = ray.st == kStMain && ray.mode == kAdvJump, isNull = ray.st == kStRegion && ray.ri == -1;
+#if VRM_FAST_LA
+			// 8: longest-axis stepping (stored-region entry, loop head, a voxel test of the current iteration)
+			const bool isLa = ray.st == kStHead || (ray.st == kStMain && ray.mode == kAdvNone) || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
+			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : (isLa ? 8u : 4u))) : 0u;
+#else
 			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : 4u)) : 0u;
+#endif
 			const unsigned all = __reduce_or_sync(0xFFFFFFFFu, cls);
 			if (all == 0u)
 			{
@@ -927,6 +948,21 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				if (ray.st == kStHit) ray.do_hit(c);
 				continue;
 			}
+#if VRM_FAST_LA
+			if (all == 8u)
+			{
+				for (;;)
+				{
+					ray.fast_la(c);
+					if (VRM_FAST_LA & 4) break;
+					const bool la = ray.st == kStHead || (ray.st == kStMain && ray.mode == kAdvNone) || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
+					const unsigned stay = __ballot_sync(0xFFFFFFFFu, la);
+					const unsigned leave = __ballot_sync(0xFFFFFFFFu, ray.st <= kStHead && !la);
+					if (leave != 0u || stay == 0u) break;
+				}
+				continue;
+			}
+#endif
 #if VRM_FAST_LOOPS
 			// The warp stays in a fast block for as long as every marching lane still qualifies (two votes per pass instead of the
 			// classification above): fast_jump leaves a lane in kStMain / kAdvJump, or in kStRegion / kStHead / kStHit; fast_nullskip
