@@ -443,7 +443,7 @@ extern "C" int sim_debug_ray(void* h, const float* ray, int algorithm, long from
 		while (rayState.st != kStDone && n < from + count)
 		{
 			if (n >= from)
-				printf("step %ld st %d mode %d shadow %d ureg %u %u %u o %.9g %.9g %.9g  d %.9g %.9g %.9g exist %llu/%llu\n", n, rayState.st, rayState.mode, (int)rayState.shadow(),
+				printf("step %ld st %d shadow %d ureg %u %u %u o %.9g %.9g %.9g  d %.9g %.9g %.9g exist %llu/%llu\n", n, rayState.st, (int)rayState.shadow(),
 				       rayState.ur[0], rayState.ur[1], rayState.ur[2], rayState.o[0], rayState.o[1], rayState.o[2], rayState.d[0], rayState.d[1], rayState.d[2],
 				       c.st.nExist, c.st.nExistFalse);
 			rayState.step(c);
@@ -536,7 +536,7 @@ extern "C" int sim_warp_profile(void* h, const float* cam, const float* tr, uint
 				for (int l = 0; l < 32; l++)
 				{
 					const uint32_t x = tx * 8 + (l & 7), y = (uint32_t)ty * 4 + (l >> 3);
-					ray[l].st = kStDone; ray[l].result = 0; ray[l].mode = 0;
+					ray[l].st = kStDone; ray[l].result = 0;
 					if (x < W && y < H)
 					{
 						float o[3], d[3];
@@ -556,7 +556,11 @@ extern "C" int sim_warp_profile(void* h, const float* cam, const float* tr, uint
 						{
 						case kStRegion: cat = ray[l].ri == -1 ? 6 : 0; break;
 						case kStHead: cat = 1; break;
-						case kStMain: cat = ray[l].mode == kAdvNone ? 2 : (ray[l].mode == kAdvJump ? 3 : (ray[l].mode == kAdvNext ? 4 : (ray[l].mode == kAdvCluster ? 5 : 6))); break;
+						case kAdvNone: cat = 2; break;
+						case kAdvJump: cat = 3; break;
+						case kAdvNext: cat = 4; break;
+						case kAdvCluster: cat = 5; break;
+						case kAdvRegion: cat = 6; break;
 						case kStHit: cat = 7; anyHit = true; break;
 						default: cat = 8; break;
 						}

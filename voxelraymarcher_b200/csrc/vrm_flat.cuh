@@ -44,14 +44,16 @@
 namespace vrm
 {
 
+// ONE state word per ray: values 0..4 are "kStMain" -- the value IS the AdvMode the next step starts with (so `is a cluster jump next`
+// is one compare, and the word the warp votes on classifies a lane completely) -- then the other blocks.  st <= kStHead: marching.
 enum FlatState : int
 {
-	kStMain = 0,
-	kStRegion = 1,
-	kStHead = 2,
-	kStHit = 3,
-	kStDone = 4,
-	kStPark = 5   // kPpDefer: the ray met the ping-pong pathology; its lane stops and the caller parks it for resume_kernel
+	kStMainLast = 4,  // st <= kStMainLast: kStMain, st = kAdvNone / kAdvNext / kAdvCluster / kAdvJump / kAdvRegion
+	kStRegion = 5,
+	kStHead = 6,
+	kStHit = 7,
+	kStDone = 8,
+	kStPark = 9   // kPpDefer: the ray met the ping-pong pathology; its lane stops and the caller parks it for resume_kernel
 };
 
 // What the advance of a kStMain step moves to.  All are "t_i = (next_i - o_i) / dir_i, o += (min t [+ EPSILON]) * dir".
@@ -183,14 +185,13 @@ struct FlatRay
 	RegionRef<ST> r;      // hash table: the region's descriptor (the VCS addresses everything from ri)
 	uint32_t sh[3];       // walk slot -> shift of its coordinate inside a storage code (VCS: 6/3/0 per world x/y/z; hash key: 14/7/0)
 	uint32_t rs[3];       // walk slot -> stride of its coordinate in the region table (1, D, D*D per world x/y/z)
-	int st;
-	int mode;             // AdvMode of the next kStMain step; a pending hit (kStHit) keeps its packed normal / shadow-routine bits here
+	int st;               // FlatState; 0..4 = kStMain with that AdvMode
 	uint32_t fl;          // kFl* bits
 	// longest-axis state (slot 0 = longest axis).  g is also "the voxel under the ray" of the other advances.
 	float ro[3];          // ray origin (rayMarchVoxelGridLongestAxis' `ray`); a pending hit keeps its position here
 	int g[3];
 	int ad1, ad2;         // axisDiff of the middle / shortest slot (slot 0's is the sign of d[0])
-	uint32_t seq;         // slots still to test this iteration, two bits each, first in the low bits; slot 0 is always the last
+	uint32_t seq;         // slots still to test this iteration, two bits each, first in the low bits; slot 0 is always the last.  A pending hit (kStHit) keeps its packed normal / shadow-routine bits here
 	// `result` = voxel colour (kStHit) -> shaded colour waiting for its shadow ray -> final pixel colour (kStDone).
 	uint32_t result;
 
@@ -241,7 +242,7 @@ struct FlatRay
 	// rayMarchVoxelScene / rayMarchVoxelSceneLongestAxis up to the first region (Renderer.cuh:338-378, 917-954)
 	VRM_HD void start_primary(RayCtx<ST, STATS>& c, const float* originW, const float* dirW, float scale)
 	{
-		fl = 0; result = 0; mode = kAdvNext; ri = -2; seq = 0; ad1 = ad2 = 0;
+		fl = 0; result = 0; ri = -2; seq = 0; ad1 = ad2 = 0;
 		g[0] = g[1] = g[2] = 0; ro[0] = ro[1] = ro[2] = 0.0f;
 		PermRuntime p;
 		p.a0 = 0; p.a1 = 1; p.a2 = 2;
@@ -303,21 +304,21 @@ struct FlatRay
 		}
 		result = col;
 		ro[0] = p0; ro[1] = p1; ro[2] = p2;
-		mode = nAxisW | (nSign < 0.0f ? 4 : 0) | (laKind ? 8 : 0);
+		seq = (uint32_t)(nAxisW | (nSign < 0.0f ? 4 : 0) | (laKind ? 8 : 0));
 		st = kStHit;
 	}
 
 	// the pending hit's lighting: where its shadow ray starts (WORLD axes) and the colour that survives when the light is visible
 	VRM_HD void shade_hit(RayCtx<ST, STATS>& c, ShadowStart& ss) const
 	{
-		const int nAxisW = mode & 3;
-		const float nSign = (mode & 4) ? -1.0f : 1.0f;
+		const int nAxisW = (int)(seq & 3u);
+		const float nSign = (seq & 4u) ? -1.0f : 1.0f;
 		const PermRuntime p = unpack_perm(fl);
 		const int minC = c.sv.minCoord;
 		const int reg[3] = {(int)ur[0] + minC, (int)ur[1] + minC, (int)ur[2] + minC};
 		to_world(p, ro, ss.hitW); to_world(p, reg, ss.regW);
 		ss.lit = apply_lighting_flat(c.light, c.translation, result, nAxisW, nSign, ss.hitW, ss.regW);
-		ss.la = (kLA && (mode & 8) != 0) ? 1 : 0;
+		ss.la = (kLA && (seq & 8u) != 0) ? 1 : 0;
 	}
 
 	// isInShadowOriginalRayMarch / isInShadowRayMarchVoxelSceneLongestAxis up to their first region (Renderer.cuh:174-199, 633-657): the
@@ -327,7 +328,7 @@ struct FlatRay
 		const bool laKind = kLA && ss.la != 0;
 		result = ss.lit;
 		fl = kFlShadow | (laKind ? kFlShadowLA : 0u);
-		mode = kAdvNext; seq = 0; ad1 = ad2 = 0; ri = -2;
+		seq = 0; ad1 = ad2 = 0; ri = -2;
 		g[0] = g[1] = g[2] = 0; ro[0] = ro[1] = ro[2] = 0.0f;  // (every one of these is rewritten before it is read; a fresh ray of the shadow kernel starts defined)
 		PermRuntime p;
 		p.a0 = 0; p.a1 = 1; p.a2 = 2;
@@ -367,7 +368,7 @@ struct FlatRay
 	VRM_HD void do_region(RayCtx<ST, STATS>& c)
 	{
 		if (ri == -2) { finish(shadow() ? result : 0u); return; }  // left the scene: background / not shadowed
-		if (ri == -1) { mode = kAdvRegion; st = kStMain; return; }  // null region: skip to its edge through the advance site
+		if (ri == -1) { st = kAdvRegion; return; }  // null region: skip to its edge through the advance site
 		r = load_region<ST>(c.sv, ri);
 		bool la = false;
 		if constexpr (kLA) la = !shadowOriginal();
@@ -382,7 +383,7 @@ struct FlatRay
 			ad2 = (int)ro[2] - g[2];
 			st = kStHead;
 		}
-		else { mode = kAdvNext; st = kStMain; }  // the region march starts with one step before the first test (Renderer.cuh:269-280)
+		else st = kAdvNext;  // the region march starts with one step before the first test (Renderer.cuh:269-280)
 	}
 
 	// ---- kStHead (longest axis): Renderer.cuh:787-805 ------------------------------------------------------------------
@@ -392,8 +393,7 @@ struct FlatRay
 		if (!grid_in_region(g[0] + ad0, g[1] + ad1, g[2] + ad2))
 		{
 			// Renderer.cuh:911-914: finish the region with the original algorithm from oldRay's origin (o already is it)
-			mode = kAdvNext;
-			st = kStMain;
+			st = kAdvNext;
 			return;
 		}
 		if (ad2 != 0 && ad1 != 0)
@@ -407,8 +407,7 @@ struct FlatRay
 		else if (ad1 != 0) seq = 1u;
 		else if (ad2 != 0) seq = 2u;
 		else seq = 0u;
-		mode = kAdvNone;
-		st = kStMain;
+		st = kAdvNone;
 	}
 
 	// ---- the voxel test: doesVoxelSpaceExist + lookupVoxel on region-local walk-space coordinates ---------------------------
@@ -541,7 +540,7 @@ struct FlatRay
 	{
 		if ((VRM_FAST_LA & 2) == 0) { if (st == kStRegion) do_region(c); }  // (ri != -1: the caller keeps null regions for fast_nullskip)
 		if (st == kStHead) do_head();
-		if (st == kStMain && mode == kAdvNone) do_main<false, kPpOff, true>(c);
+		if (st == kAdvNone) do_main<false, kPpOff, true>(c);
 	}
 
 	// do_region with ri == -1 followed by do_main with mode == kAdvRegion: skip to the null region's edge, no +EPSILON
@@ -553,7 +552,6 @@ struct FlatRay
 		if (!(fminf(fabsf(x0), fminf(fabsf(x1), fabsf(x2))) >= thr)) return false;
 		const float a0 = div_by_const(x0, d[0], rd[0]), a1 = div_by_const(x1, d[1], rd[1]), a2 = div_by_const(x2, d[2], rd[2]);
 		const float s = min3(a0, a1, a2);
-		mode = kAdvRegion;
 		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
 		change_region(c);
 		return true;
@@ -566,6 +564,7 @@ struct FlatRay
 	VRM_HD void do_main(RayCtx<ST, STATS>& c)
 	{
 		int slot = 0;
+		const int mode = st;  // the AdvMode this step starts with (st <= kStMainLast here)
 		const bool test = kLA && (TESTONLY || mode == kAdvNone);
 		const bool jump = kLA && !TESTONLY && mode == kAdvJump;
 		if (!test)
@@ -666,7 +665,7 @@ struct FlatRay
 		// no voxel here: decide the next micro-step
 		if (!test)
 		{
-			if (!jump) mode = e ? kAdvNext : kAdvCluster;
+			if (!jump) st = e ? kAdvNext : kAdvCluster;
 			else if (e)
 			{
 				if constexpr (kLA) resnap_after_jump();
@@ -681,7 +680,7 @@ struct FlatRay
 				// performVoxelSpaceJump (Renderer.cuh:808-810 -> 696): its while condition repeats the exist check of the failed
 				// test on the same voxel -- same answer, only the counter sees it
 				if (STATS) { c.st.nExist++; c.st.nExistFalse++; }
-				mode = kAdvJump;
+				st = kAdvJump;
 			}
 			else if (slot == 0)
 			{
@@ -711,7 +710,7 @@ struct FlatRay
 #if defined(__CUDA_ARCH__)
 		DeferHeader* h = static_cast<DeferHeader*>(c.deferQueue);
 		const unsigned int slot = atomicAdd(&h->count, 1u);
-		st = kStMain;
+		st = kAdvJump;  // only a cluster jump parks (do_main): the step that parked is redone
 		if (slot >= h->capacity) return -1;
 		Deferred* items = reinterpret_cast<Deferred*>(h + 1);
 		items[slot].ray = *this;
@@ -720,7 +719,7 @@ struct FlatRay
 		st = kStDone;
 		return (int)slot;
 #else
-		st = kStMain;
+		st = kAdvJump;
 		return -1;
 #endif
 	}
@@ -740,20 +739,20 @@ struct FlatRay
 	// the cycles.  The span keeps the coordinate inside its voxel and its binade.
 	struct Discrete
 	{
-		int st, mode, g0, g1, g2, ad1, ad2;
+		int st, g0, g1, g2, ad1, ad2;
 		int32_t ri;
 		uint32_t ur0, ur1, ur2, seq, fl, o1, o2;
 	};
 	VRM_HD Discrete discrete() const
 	{
 		Discrete k;
-		k.st = st; k.mode = mode; k.g0 = g[0]; k.g1 = g[1]; k.g2 = g[2]; k.ad1 = ad1; k.ad2 = ad2; k.ri = ri;
+		k.st = st; k.g0 = g[0]; k.g1 = g[1]; k.g2 = g[2]; k.ad1 = ad1; k.ad2 = ad2; k.ri = ri;
 		k.ur0 = ur[0]; k.ur1 = ur[1]; k.ur2 = ur[2]; k.seq = seq; k.fl = fl & ~kFlEqMask; k.o1 = float_bits(o[1]); k.o2 = float_bits(o[2]);
 		return k;
 	}
 	static VRM_HD bool same_discrete(const Discrete& a, const Discrete& b)
 	{
-		return a.st == b.st && a.mode == b.mode && a.g0 == b.g0 && a.g1 == b.g1 && a.g2 == b.g2 && a.ad1 == b.ad1 && a.ad2 == b.ad2 && a.ri == b.ri &&
+		return a.st == b.st && a.g0 == b.g0 && a.g1 == b.g1 && a.g2 == b.g2 && a.ad1 == b.ad1 && a.ad2 == b.ad2 && a.ri == b.ri &&
 		       a.ur0 == b.ur0 && a.ur1 == b.ur1 && a.ur2 == b.ur2 && a.seq == b.seq && a.fl == b.fl && a.o1 == b.o1 && a.o2 == b.o2;
 	}
 
@@ -763,15 +762,15 @@ struct FlatRay
 	{
 		if constexpr (kLA)
 		{
-			if (!(st == kStMain && mode == kAdvJump)) return false;
+			if (st != kAdvJump) return false;
 			do_main<true>(c);
 			if (st != kStRegion) return false;
 			do_region(c);
 			if (st != kStHead) return false;
 			do_head();
-			if (!(st == kStMain && mode == kAdvNone)) return false;
+			if (st != kAdvNone) return false;
 			do_main<true>(c);
-			return st == kStMain && mode == kAdvJump;
+			return st == kAdvJump;
 		}
 		return false;
 	}
@@ -866,7 +865,7 @@ struct FlatRay
 		if (st == kStHit) do_hit(c);
 		if (st == kStRegion) do_region(c);
 		if constexpr (kLA) { if (st == kStHead) do_head(); }
-		if (st == kStMain) do_main<false, PP>(c);
+		if (st <= kStMainLast) do_main<false, PP>(c);
 		return st == kStDone;
 	}
 
@@ -877,9 +876,9 @@ struct FlatRay
 	{
 		if constexpr (kLA && ST == kStorageVcs)
 		{
-			if (st == kStMain && mode == kAdvJump) { if (fast_jump(c)) return st == kStDone; }
+			if (st == kAdvJump) { if (fast_jump(c)) return st == kStDone; }
 			else if (st == kStRegion && ri == -1) { if (fast_nullskip(c)) return st == kStDone; }
-			else if (st == kStHead || (st == kStMain && mode == kAdvNone) || ((VRM_FAST_LA & 2) == 0 && st == kStRegion)) { fast_la(c); return st == kStDone; }
+			else if (st == kStHead || st == kAdvNone || ((VRM_FAST_LA & 2) == 0 && st == kStRegion)) { fast_la(c); return st == kStDone; }
 		}
 		return step<PP>(c);
 	}
@@ -890,7 +889,7 @@ struct FlatRay
 	{
 		if (st == kStRegion) do_region(c);
 		if constexpr (kLA) { if (st == kStHead) do_head(); }
-		if (st == kStMain) do_main<false, PP>(c);
+		if (st <= kStMainLast) do_main<false, PP>(c);
 	}
 };
 
@@ -903,15 +902,15 @@ VRM_HD void warp_march_pass(RayCtx<ST, STATS>& c, FlatRay<ST, ALGO, STATS>& ray)
 {
 #if defined(__CUDA_ARCH__) && (VRM_REGION_VOTE > 0 || VRM_HEAD_VOTE > 0)
 	const unsigned wantRegion = __ballot_sync(0xFFFFFFFFu, ray.st == kStRegion);
-	const unsigned others = __ballot_sync(0xFFFFFFFFu, ray.st == kStHead || ray.st == kStMain);
+	const unsigned others = __ballot_sync(0xFFFFFFFFu, ray.st == kStHead || ray.st <= kStMainLast);
 	if (wantRegion != 0u && (VRM_REGION_VOTE <= 0 || __popc(wantRegion) >= VRM_REGION_VOTE || others == 0u)) { if (ray.st == kStRegion) ray.do_region(c); }
 	if constexpr (ALGO != kAlgoOriginal)
 	{
 		const unsigned wantHead = __ballot_sync(0xFFFFFFFFu, ray.st == kStHead);
-		const unsigned wantMain = __ballot_sync(0xFFFFFFFFu, ray.st == kStMain);
+		const unsigned wantMain = __ballot_sync(0xFFFFFFFFu, ray.st <= kStMainLast);
 		if (wantHead != 0u && (VRM_HEAD_VOTE <= 0 || __popc(wantHead) >= VRM_HEAD_VOTE || wantMain == 0u)) { if (ray.st == kStHead) ray.do_head(); }
 	}
-	if (ray.st == kStMain) ray.template do_main<false, PP>(c);
+	if (ray.st <= kStMainLast) ray.template do_main<false, PP>(c);
 #else
 	if (ray.st <= kStHead) ray.template step_marching<PP>(c);
 #endif
@@ -939,10 +938,10 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 		for (;;)
 		{
 			// what the warp's marching lanes (kStMain, kStRegion, kStHead) are about to do: 1 a cluster jump, 2 a null-region skip, 4 anything else
-			const bool isJump = ray.st == kStMain && ray.mode == kAdvJump, isNull = ray.st == kStRegion && ray.ri == -1;
+			const bool isJump = ray.st == kAdvJump, isNull = ray.st == kStRegion && ray.ri == -1;
 #if VRM_FAST_LA
 			// 8: longest-axis stepping (stored-region entry, loop head, a voxel test of the current iteration)
-			const bool isLa = ray.st == kStHead || (ray.st == kStMain && ray.mode == kAdvNone) || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
+			const bool isLa = ray.st == kStHead || ray.st == kAdvNone || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
 			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : (isLa ? 8u : 4u))) : 0u;
 #else
 			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : 4u)) : 0u;
@@ -962,7 +961,7 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				{
 					ray.fast_la(c);
 					if (VRM_FAST_LA & 4) break;
-					const bool la = ray.st == kStHead || (ray.st == kStMain && ray.mode == kAdvNone) || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
+					const bool la = ray.st == kStHead || ray.st == kAdvNone || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
 					const unsigned stay = __ballot_sync(0xFFFFFFFFu, la);
 					const unsigned leave = __ballot_sync(0xFFFFFFFFu, ray.st <= kStHead && !la);
 					if (leave != 0u || stay == 0u) break;
@@ -979,8 +978,8 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				for (;;)
 				{
 					bool ok = true;
-					if (ray.st == kStMain) ok = ray.fast_jump(c);
-					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kStMain);
+					if (ray.st == kAdvJump) ok = ray.fast_jump(c);
+					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kAdvJump);
 					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || ray.st == kStRegion || ray.st == kStHead);
 					if (leave != 0u || stay == 0u) { generic = __any_sync(0xFFFFFFFFu, !ok); break; }
 				}

@@ -544,25 +544,27 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 	bool exhausted = false;  // warp-uniform: the queue has run dry
 	for (;;)
 	{
-		const int st = ray.st;
-		const bool votes = !(st == kStDone && exhausted);
+		// the block a lane wants to run: 0 main (any advance mode), 1 region, 2 head, 3 hit, 4 done (5 parked: never, kPpOff)
+		constexpr int bMain = 0, bRegion = 1, bHit = 3, bDone = 4;
+		const int st = ray.st <= kStMainLast ? bMain : ray.st - kStMainLast;
+		const bool votes = !(st == bDone && exhausted);
 		const int ballotState = votes ? st : 7;
 		const unsigned peers = __match_any_sync(0xFFFFFFFFu, ballotState);
 		const int key = votes ? (((32 - __popc(peers)) << 3) | st) : ((32 << 3) | 7);
 		const int best = __reduce_min_sync(0xFFFFFFFFu, key);
 		const int run = best & 7;
 		if (run == 7) break;  // every lane is idle and the queue is dry
-		if (run == kStDone)
+		if (run == bDone)
 		{
 			// refill: the idle lanes are the largest group
-			const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, st == kStDone);
+			const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, st == bDone);
 			const int want = __popc(idleMask);
 			const int leader = __ffs(idleMask) - 1;
 			unsigned base = 0;
 			if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned)want);
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
 			if (base + want >= total) exhausted = true;
-			if (st == kStDone)
+			if (st == bDone)
 			{
 				const unsigned slot = base + __popc(idleMask & ((1u << lane) - 1u));
 				if (slot < total)
@@ -597,9 +599,9 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 		}
 		if (st == run)
 		{
-			if (run == kStMain) ray.template do_main<false, kPpOff>(c);
-			else if (run == kStRegion) ray.do_region(c);
-			else if (run == kStHit) ray.do_hit(c);
+			if (run == bMain) ray.template do_main<false, kPpOff>(c);
+			else if (run == bRegion) ray.do_region(c);
+			else if (run == bHit) ray.do_hit(c);
 			else if constexpr (ALGO != kAlgoOriginal) ray.do_head();
 			if (ray.st == kStDone)
 			{
