@@ -7,10 +7,10 @@ scene at 1/2/4/8 B200).
 
 A step = one pass of the hot path over one batch of synthetic input = ONE 3840x2160 frame per GPU of the procedural
 512^3 terrain (~32 M voxels, BASELINE.json configs[2]) with the reference CLI's default combination (Voxel Cluster Store +
-longest-axis traversal, Main.cu:45-68), shadows on.  Frame (step k, rank r) is view ((k * N + r) * 25) mod 64 of a 64-view
+longest-axis traversal, Main.cu:45-68), shadows on.  Frame (step k, rank r) is view (25 k + r * 64 / N) mod 64 of a 64-view
 orbit whose view 0 is SURVEY.md 8d-3's camera: every rank renders DIFFERENT frames (sharding must not be measured on
 replicated identical work), and the stride of 25 walks the orbit in a low-discrepancy order so that any K consecutive frames
-sample it evenly and the mean frame cost is the same at every N.  The named single view itself is timed separately
+sample it evenly and every rank's mean frame cost is the single GPU's.  The named single view itself is timed separately
 (`single_view`).  The structure is built once per GPU, on the GPU, before the timed region and is replicated on every rank.
 
 N > 1: the path's only exchange step -- finished frames arriving on rank 0 -- is fused into the render kernels (stores into rank
@@ -49,7 +49,11 @@ VIEW_STRIDE = 25     # odd: a permutation of the 64 views in a low-discrepancy o
 
 
 def view_of(step: int, rank: int, world: int) -> int:
-    return ((step * world + rank) * VIEW_STRIDE) % ORBIT_VIEWS
+    """Every rank walks the SAME low-discrepancy sequence of orbit views (stride 25), rotated by rank * 64 / N: at any step the N ranks
+    render N different views spaced evenly around the orbit, and every rank's K frames sample the orbit exactly as the single GPU's do
+    (the first form, ((step * N + rank) * 25) mod 64, gave a rank only 64 / gcd(64, 25 N) = 8 distinct views at N = 8, whose mean cost
+    differed by +-3 % between ranks: a sampling artefact in a max-over-ranks time)."""
+    return (step * VIEW_STRIDE + rank * (ORBIT_VIEWS // max(1, world))) % ORBIT_VIEWS
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -200,7 +204,7 @@ def _orbit_args(view):
 def workload_config():
     return {"workload": f"terrain{SCENE_SIZE}_4k_{STORAGE}_{ALGORITHM}", "scene": f"procedural {SCENE_SIZE}^3 terrain, seed {SCENE_SEED}, ~32 M voxels (BASELINE.json configs[2])",
             "resolution": f"{WIDTH}x{HEIGHT}", "storage": STORAGE, "algorithm": ALGORITHM, "shadows": True,
-            "views": "one frame per GPU per step: (step k, rank r) renders view ((k*N + r) * 25) mod 64 of a 64-view orbit of radius 498 at height 352 around (256,64,256); "
+            "views": "one frame per GPU per step: (step k, rank r) renders view (25*k + r*64/N) mod 64 of a 64-view orbit of radius 498 at height 352 around (256,64,256); "
                      "view 0 = SURVEY.md 8d-3's camera (-96,352,-96), fov 60", "l2": "flushed between steps (512 MiB write, outside the per-step event pairs)",
             "parallelism": "frames sharded across GPUs (one per GPU per step, all different), structure replicated, frames stored into rank 0's buffer by the render kernels "
                            "(NVLink peer memory) + a completion word per rank; no collective on the data path"}

@@ -184,6 +184,8 @@ int vrm_scene_create(int device, vrm_scene** out)
 	if (const char* mode = getenv("VRM_RENDER_MODE")) s->renderMode = atoi(mode);
 	if (const char* form = getenv("VRM_SHADOW_FORM")) { const int f = atoi(form); if (f >= 0 && f <= 2) s->shadowForm = f; }
 	if (const char* lp = getenv("VRM_L2_PERSIST")) s->l2Persist = atoi(lp) != 0;
+	if (const char* pd = getenv("VRM_PINNED_DMA")) s->pinnedDma = atoi(pd);
+	if (const char* ws = getenv("VRM_WSTORE_REMOTE")) s->wstoreRemote = atoi(ws) != 0;
 	if (const char* bb = getenv("VRM_VIEW_BATCH_BYTES")) { long long v = atoll(bb); if (v > 0) s->viewBatchBytes = (size_t)v; }
 	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }
 	s->stream = s->ownStream;
@@ -207,6 +209,7 @@ int vrm_scene_destroy(vrm_scene* s)
 	if (s->ev1) cudaEventDestroy(s->ev1);
 	if (s->ownStream) cudaStreamDestroy(s->ownStream);
 	if (s->copyStream) cudaStreamDestroy(s->copyStream);
+	if (s->d_dmaFrame) cudaFree(s->d_dmaFrame);
 	for (int i = 0; i < 2; i++)
 	{
 		if (s->evRendered[i]) cudaEventDestroy(s->evRendered[i]);
@@ -396,22 +399,47 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 		if (!d_rgb) { s->lastError = "page-locked staging frame is not mapped"; return VRM_ERR_CUDA; }
 	}
 	if (copyHits) { p = s->d_hits; rc = ensure(s, &p, &s->hitsBytes, px * 16); s->d_hits = static_cast<int32_t*>(p); if (rc) return rc; d_hits = s->d_hits; }
+	// Page-locked frame, copy-engine form (s->pinnedDma bands): the kernels render horizontal bands into a frame in device memory (per-warp
+	// stores, no PCIe traffic from the SMs) and the copy engine sends band k while band k+1 renders.  Full-line DMA writes instead of
+	// 96-byte partial-line stores from the SMs: what keeps the end-to-end rate up when eight GPUs write frames into host memory at once.
+	const bool dmaRgb = !stageRgb && s->pinnedDma > 0 && px * 3 >= (size_t(1) << 20);
+	uint8_t* h_dst = rgb_out;
+	if (dmaRgb)
+	{
+		if (s->dmaFrameBytes < px * 3)
+		{
+			VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+			if (s->d_dmaFrame) cudaFree(s->d_dmaFrame);
+			s->d_dmaFrame = nullptr; s->dmaFrameBytes = 0;
+			VRM_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&s->d_dmaFrame), px * 3));
+			s->dmaFrameBytes = px * 3;
+		}
+		if (!s->copyStream) VRM_CUDA(s, cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+		d_rgb = s->d_dmaFrame;
+	}
 	rc = upload_cameras(s, camera, 1);
 	if (rc) return rc;
 	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
 	constexpr int kMaxBands = 8;
 	int bands = 1;
 	if (stageRgb) { bands = (int)(px * 3 / (size_t(6) << 20)); if (bands < 1) bands = 1; if (bands > 4) bands = 4; }  // >= 6 MB per band, four bands at most (every band is a launch sequence of its own)
+	if (dmaRgb) { bands = s->pinnedDma; if (bands > kMaxBands) bands = kMaxBands; while (bands > 1 && px * 3 / bands < (size_t(2) << 20)) bands--; }
 	uint32_t bandEnd[kMaxBands];
 	for (int b = 0; b < bands; b++) bandEnd[b] = b == bands - 1 ? height : (uint32_t)(((uint64_t)height * (b + 1) / bands + 7) & ~7ull);
-	if (stageRgb) for (int b = 0; b < bands; b++) if (!s->evBand[b]) VRM_CUDA(s, cudaEventCreateWithFlags(&s->evBand[b], cudaEventDisableTiming));
+	if (stageRgb || dmaRgb) for (int b = 0; b < bands; b++) if (!s->evBand[b]) VRM_CUDA(s, cudaEventCreateWithFlags(&s->evBand[b], cudaEventDisableTiming));
 	for (int b = 0; b < bands; b++)
 	{
 		const uint32_t y0 = b ? bandEnd[b - 1] : 0u, y1 = bandEnd[b] < height ? bandEnd[b] : height;
 		if (y1 <= y0) continue;
 		rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, d_rgb, d_hits, y0, y1);
 		if (rc) return rc;
-		if (stageRgb) VRM_CUDA(s, cudaEventRecord(s->evBand[b], s->stream));
+		if (stageRgb || dmaRgb) VRM_CUDA(s, cudaEventRecord(s->evBand[b], s->stream));
+		if (dmaRgb)
+		{
+			const size_t off = (size_t)y0 * width * 3, bytes = (size_t)(y1 - y0) * width * 3;
+			VRM_CUDA(s, cudaStreamWaitEvent(s->copyStream, s->evBand[b], 0));
+			VRM_CUDA(s, cudaMemcpyAsync(h_dst + off, s->d_dmaFrame + off, bytes, cudaMemcpyDeviceToHost, s->copyStream));
+		}
 	}
 	VRM_CUDA(s, cudaEventRecord(s->ev1, s->stream));
 	if (copyHits) VRM_CUDA(s, cudaMemcpyAsync(hits_out, s->d_hits, px * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -426,6 +454,7 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 		}
 	}
 	VRM_CUDA(s, cudaStreamSynchronize(s->stream));
+	if (dmaRgb) VRM_CUDA(s, cudaStreamSynchronize(s->copyStream));
 	if (kernel_ms) VRM_CUDA(s, cudaEventElapsedTime(kernel_ms, s->ev0, s->ev1));
 	return VRM_OK;
 }

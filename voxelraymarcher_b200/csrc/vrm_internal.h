@@ -88,6 +88,9 @@ struct vrm_scene
 	void* d_shadowItems = nullptr;    size_t shadowCap = 0;
 	unsigned int* d_shadowCtl = nullptr;
 
+	uint8_t* d_dmaFrame = nullptr;    size_t dmaFrameBytes = 0;    // vrm_render into a page-locked buffer, copy-engine form
+	int pinnedDma = 0;                // bands of that form (VRM_PINNED_DMA); 0 = the kernels store into the mapped buffer themselves
+	bool wstoreRemote = false;        // A/B: per-warp stores for frames outside this GPU's memory too (VRM_WSTORE_REMOTE)
 	uint8_t* d_localFrame = nullptr;  size_t localFrameBytes = 0;  // frames of a queue-pipeline launch whose destination is not local memory
 	int shadowForm = -1;              // shadow kernel: -1 per-combination default, 0 nested loops, 1 state machine, 2 state machine with lane-level refill (VRM_SHADOW_FORM)
 	int statsMode = 0;                // 0 off, 1 event counters comparable with the reference (every shadow ray traced), 2 counters of the work as executed

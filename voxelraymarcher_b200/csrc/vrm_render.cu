@@ -1151,7 +1151,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 		cudaPointerAttributes at;
 		const bool local = cudaPointerGetAttributes(&at, d_rgb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == s->device;
 		cudaGetLastError();
-		a.rgbLocal = local ? 1u : 0u;
+		a.rgbLocal = (local || s->wstoreRemote) ? 1u : 0u;
 		viaLocal = !local && (mode == 1 || mode == 4) && s->light.useShadows;
 	}
 	const size_t frameBytes = (size_t)W * H * 3;
