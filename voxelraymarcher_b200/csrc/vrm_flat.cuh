@@ -93,6 +93,9 @@ constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
 #ifndef VRM_FAST_LA
 #define VRM_FAST_LA 7      // a third warp-uniform block: longest-axis stepping (FlatRay::fast_la); A/B bits: 2 = without the stored-region entry, 4 = without the inner loop
 #endif
+#ifndef VRM_FAST_ENTER
+#define VRM_FAST_ENTER 0   // 1: fast_jump / fast_nullskip run a stored region's entry block in the pass that changed region (A/B: 1.338 vs 1.332 ms, off)
+#endif
 #ifndef VRM_FAST_LOOPS
 #define VRM_FAST_LOOPS 1   // the warp stays inside a fast block while every marching lane still qualifies
 #endif
@@ -520,7 +523,7 @@ struct FlatRay
 		// follows in this very step: the next advance that can precede a hit -- another jump or the original algorithm's kAdvNext --
 		// rewrites them, a kAdvCluster only ever follows a kAdvNext, and longest-axis test hits take their normal from the slot.  So
 		// they are formed at the hit (0.3 times per ray) instead of at each of the ~9 jumps per ray.
-		if (!ray_in_region(o)) { change_region(c); return true; }
+		if (!ray_in_region(o)) { change_region(c); enter_stored_region(c); return true; }
 		g[0] = (int)o[0]; g[1] = (int)o[1]; g[2] = (int)o[2];
 		uint32_t col;
 		const bool e = voxel_test(c, g[0], g[1], g[2], col);
@@ -531,6 +534,16 @@ struct FlatRay
 		}
 		else if (e) resnap_after_jump();
 		return true;
+	}
+
+	// A fast block that changed region runs the new region's entry block right away when the region is stored (prologue of the
+	// longest-axis march): the lane is then at the loop head and its next pass can be a longest-axis-stepping pass instead of a
+	// generic one (stored-region entries were part of 12 % of the passes, nearly all of them generic because of that one block).
+	VRM_HD void enter_stored_region(RayCtx<ST, STATS>& c)
+	{
+#if VRM_FAST_ENTER
+		if (st == kStRegion && ri >= 0) do_region(c);
+#endif
 	}
 
 	// Longest-axis stepping: every marching lane of the warp is entering a stored region, at the loop head, or has voxel tests of its
@@ -554,6 +567,7 @@ struct FlatRay
 		const float s = min3(a0, a1, a2);
 		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
 		change_region(c);
+		enter_stored_region(c);
 		return true;
 	}
 
@@ -992,7 +1006,7 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 					bool ok = true;
 					if (ray.st == kStRegion) ok = ray.fast_nullskip(c);
 					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kStRegion && ray.ri == -1);
-					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || (ray.st == kStRegion && ray.ri != -1));
+					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || (ray.st <= kStHead && !(ray.st == kStRegion && ray.ri == -1)));
 					if (leave != 0u || stay == 0u) { generic = __any_sync(0xFFFFFFFFu, !ok); break; }
 				}
 				continue;

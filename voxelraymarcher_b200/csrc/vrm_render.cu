@@ -538,6 +538,7 @@ __global__ void __launch_bounds__(kPersistThreads) render_scheduled_kernel(const
 	c.hitOut = nullptr;
 	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
 	c.reset();
+	c.skipDead = a.skipDead;
 	FlatRay<ST, ALGO, STATS> ray;
 	ray.st = kStDone;
 	size_t pixel = 0;
@@ -1070,6 +1071,7 @@ template <int ST, int ALGO> void launch_render_t(vrm_scene* s, RenderArgs a, dim
 		if (bps < 1) bps = 1;
 	}
 	const unsigned blocks = (unsigned)(s->numSms * bps);
+	a.skipDead = s->statsMode == 1 ? 0u : 1u;
 	cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned int), s->stream);
 	if (s->statsEnabled) render_scheduled_kernel<ST, ALGO, true><<<blocks, kPersistThreads, 0, s->stream>>>(a);
 	else render_scheduled_kernel<ST, ALGO, false><<<blocks, kPersistThreads, 0, s->stream>>>(a);
