@@ -255,6 +255,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / ref_gpu / orbit legs (profiling runs)")
     ap.add_argument("--single-view", action="store_true", help="every step renders view 0 (the named single view; profiling runs)")
+    ap.add_argument("--orbit-only", action="store_true", help="only the strong-scaling leg (configs[3], the 2048^3 orbit); prints its dict (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -283,6 +284,17 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
+    if args.orbit_only:
+        stream = torch.cuda.Stream(dev)
+        torch.cuda.set_stream(stream)
+        orbit = orbit_leg(api, torch, dist, dev, local_rank, rank, world, stream)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        os.dup2(saved_stdout, 1)
+        if rank == 0:
+            print(json.dumps({"orbit_2048_strong_scaling": orbit, "n_gpus": n_gpus}), flush=True)
+        return
 
     # ---- scene: generated and built on the GPU, replicated per rank (deterministic) --------------------------------------
     warm = api.VoxelScene(local_rank)            # loads the CUDA modules and fills the memory pool: the timed build below is not a cold start
