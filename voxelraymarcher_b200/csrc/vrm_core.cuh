@@ -615,6 +615,15 @@ VRM_HD float bits_float(uint32_t u)
 #endif
 }
 
+// next_edge for a direction component that is NOT ZERO (every component of a ray whose fast-division threshold is finite): the sign
+// bit of d decides, and ceilf(v) + EPSILON = -(floorf(-v) - EPSILON) exactly (negation is exact, round-to-nearest is symmetric), so
+// the two roundings + two sums + select of next_edge become one conditional sign flip, one rounding, one sum and the flip back.
+VRM_HD float next_edge_nz(float d, float v)
+{
+	const uint32_t flip = ~float_bits(d) & 0x80000000u;
+	return bits_float(float_bits(vsub(floorf(bits_float(float_bits(v) ^ flip)), kEps)) ^ flip);
+}
+
 // ---- "crawl" fast-forward ---------------------------------------------------------------------------------------------
 // A reference pathology that dominates whole frames: a cluster skip towards a NEGATIVE direction component d_j with
 // |d_j| < ~5e-3 lands the ray EXACTLY on the cluster face (o_j + EPSILON * d_j rounds back to the face), the voxel (int)o_j
@@ -749,12 +758,15 @@ VRM_HD int32_t skip_null_regions(RayCtx<ST, STATS>& c, const P& p, float* o, con
 // The step loop shared by rayMarchVoxelGrid (Renderer.cuh:260-336, GUARD=false) and shadowRayMarchVoxelGrid
 // (Renderer.cuh:100-172, GUARD=true).  Returns the raw voxel colour or kEmpty; t[0..3] = the OUTER tX,tY,tZ,tMin
 // of the hit step (stale after a cluster skip, exactly as in the reference, SURVEY.md §7 hard part 3).
-template <int ST, bool STATS, class P, bool GUARD>
-VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const RayDir& k, const int* reg, float* t)
+// NZ: the caller knows that no direction component is zero (k.thr is finite): next_edge_nz, and the zero-direction guards of the
+// shadow routine (Renderer.cuh:113-115) are moot.
+template <int ST, bool STATS, class P, bool GUARD_, bool NZ>
+VRM_HD uint32_t march_steps_t(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const RayDir& k, const int* reg, float* t)
 {
+	constexpr bool GUARD = GUARD_ && !NZ;
 	const float* d = k.d;
 	float t0, t1, t2;
-	t_to3<GUARD>(k, next_edge(d[0], o[0]), next_edge(d[1], o[1]), next_edge(d[2], o[2]), o, t0, t1, t2);
+	t_to3<GUARD>(k, NZ ? next_edge_nz(d[0], o[0]) : next_edge(d[0], o[0]), NZ ? next_edge_nz(d[1], o[1]) : next_edge(d[1], o[1]), NZ ? next_edge_nz(d[2], o[2]) : next_edge(d[2], o[2]), o, t0, t1, t2);
 	float tMin = min3(t0, t1, t2);
 	float s = vadd(tMin, kEps);
 	o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
@@ -786,12 +798,24 @@ VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const 
 			t[0] = t0; t[1] = t1; t[2] = t2; t[3] = tMin;
 			return col;
 		}
-		t_to3<GUARD>(k, next_edge(d[0], o[0]), next_edge(d[1], o[1]), next_edge(d[2], o[2]), o, t0, t1, t2);
+		t_to3<GUARD>(k, NZ ? next_edge_nz(d[0], o[0]) : next_edge(d[0], o[0]), NZ ? next_edge_nz(d[1], o[1]) : next_edge(d[1], o[1]), NZ ? next_edge_nz(d[2], o[2]) : next_edge(d[2], o[2]), o, t0, t1, t2);
 		tMin = min3(t0, t1, t2);
 		s = vadd(tMin, kEps);
 		o[0] = along(o[0], s, d[0]); o[1] = along(o[1], s, d[1]); o[2] = along(o[2], s, d[2]);
 	}
 	return kEmpty;
+}
+
+#ifndef VRM_STEPS_NZ
+#define VRM_STEPS_NZ 1
+#endif
+template <int ST, bool STATS, class P, bool GUARD>
+VRM_HD uint32_t march_steps(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, float* o, const RayDir& k, const int* reg, float* t)
+{
+#if VRM_STEPS_NZ
+	if (k.thr == k.thr) return march_steps_t<ST, STATS, P, GUARD, true>(c, r, p, o, k, reg, t);  // per-ray constant: no direction component is zero
+#endif
+	return march_steps_t<ST, STATS, P, GUARD, false>(c, r, p, o, k, reg, t);
 }
 
 // What a primary march reports on a hit; lighting and the shadow ray are applied ONCE, in march_scene, instead of
