@@ -1,17 +1,50 @@
 #!/bin/bash
-# Round-end measurement set on a GPU box (1 GPU):  bash tools/profile_round.sh <tag>
-#   bench line (native + reference arm), the ncu launch list of the bench command, and one `--set full` capture of the
-#   dominant kernel of the headline combination and of the hash-table kernel.  Nothing printed under ncu is a bench value.
-tag=${1:-rXX}
+# Round-end measurement set on a GPU box (one GPU; round 2 ran it as call z): whole GPU test tier, captures of the final kernels (summarised on the box, merged into
+# profiles/ncu_summary.json BEFORE the bench so that its issue roof uses this build's capture), bench line + reference arm, launch list, A/B.
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${tag}_n1.json 2> gpurun_out/bench_${tag}_n1.err || echo "bench failed"
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${tag}_reference_arm.json 2> gpurun_out/bench_${tag}_reference_arm.err || echo "reference arm failed"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
-    python bench.py --steps 5 --warmup 3 --no-baselines > gpurun_out/ncu_launches_${tag}.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:render_kernel -s 2 -c 1 -o gpurun_out/prof_${tag}_vcs_la -f \
-    python tools/explore.py --iters 2 --combos vcs:longestaxis --out gpurun_out/x.json > gpurun_out/ncu_${tag}_vcs_la.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:render_kernel -s 2 -c 1 -o gpurun_out/prof_${tag}_hash_orig -f \
-    python tools/explore.py --iters 2 --combos hashtable:original --out gpurun_out/x.json > gpurun_out/ncu_${tag}_hash_orig.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:render_kernel -s 2 -c 1 -o gpurun_out/prof_${tag}_vcs_orig -f \
-    python tools/explore.py --iters 2 --combos vcs:original --out gpurun_out/x.json > gpurun_out/ncu_${tag}_vcs_orig.log 2>&1
-tail -c 600 gpurun_out/bench_${tag}_n1.json; echo; cat gpurun_out/bench_${tag}_reference_arm.json
+cd "$(dirname "$0")/.."
+export PYTHONUNBUFFERED=1
+( time timeout 1500 python -m pytest tests -m gpu -q -x --durations=5 ) > gpurun_out/r02z_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r02z_pytest.log
+tail -12 gpurun_out/r02z_pytest.log
+( VRM_RENDER_MODE=4 timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -q -x ) > gpurun_out/r02z_pytest_mode4.log 2>&1; tail -1 gpurun_out/r02z_pytest_mode4.log
+( VRM_RENDER_MODE=0 timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -q -x ) > gpurun_out/r02z_pytest_mode0.log 2>&1; tail -1 gpurun_out/r02z_pytest_mode0.log
+rm -f gpurun_out/ncu_summary.json
+bash tools/gpu_capture.sh r02z_ncu_render_vcs_longestaxis render_kernel 3 terrain512_4k_vcs_longestaxis -- python bench.py --steps 2 --warmup 3 --no-baselines --single-view
+bash tools/gpu_capture.sh r02z_ncu_render_hashtable_original render_kernel 6 terrain512_4k_hashtable_original -- python tools/explore.py --iters 2 --combos hashtable:original --out gpurun_out/x.json
+bash tools/gpu_capture.sh r02z_ncu_shadow_hashtable_original shadow_kernel 6 terrain512_4k_hashtable_original_shadow -- python tools/explore.py --iters 2 --combos hashtable:original --out gpurun_out/x.json
+bash tools/gpu_capture.sh r02z_ncu_render_vcs_original render_kernel 6 terrain512_4k_vcs_original -- python tools/explore.py --iters 2 --combos vcs:original --out gpurun_out/x.json
+bash tools/gpu_capture.sh r02z_ncu_shadow_vcs_original shadow_kernel 6 terrain512_4k_vcs_original_shadow -- python tools/explore.py --iters 2 --combos vcs:original --out gpurun_out/x.json
+bash tools/gpu_capture.sh r02z_ncu_trace_config5_vcs_longestaxis trace_kernel 2 shells1024_trace_vcs_longestaxis -- python tools/ncu_targets.py trace5 longestaxis
+bash tools/gpu_capture.sh r02z_ncu_trace_config5_shadow_refill shadow_refill_kernel 2 shells1024_trace_vcs_longestaxis_shadow -- python tools/ncu_targets.py trace5 longestaxis
+bash tools/gpu_capture.sh r02z_ncu_orbit_config4_vcs_longestaxis render_kernel 2 shells2048_orbit_vcs_longestaxis -- python tools/ncu_targets.py orbit4
+rm -f gpurun_out/x.json
+python - <<'PY'
+import json, os
+new = json.load(open("gpurun_out/ncu_summary.json")) if os.path.exists("gpurun_out/ncu_summary.json") else {}
+path = "profiles/ncu_summary.json"
+old = json.load(open(path)) if os.path.exists(path) else {}
+old.update(new)
+json.dump(old, open(path, "w"), indent=1)
+print("ncu_summary workloads updated:", sorted(new))
+PY
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02z_bench_n1.json 2> gpurun_out/r02z_bench_n1.err || { echo "bench failed"; tail -20 gpurun_out/r02z_bench_n1.err; }
+python - <<'PY'
+import json
+try:
+    d = json.load(open("gpurun_out/r02z_bench_n1.json"))
+    for k in ("value", "ms_per_step", "e2e", "single_view", "stats_per_ray", "build", "build_hashtable", "cpu_baseline", "gpu_launches"):
+        print(k, json.dumps(d.get(k))[:500])
+    print("combos", json.dumps({k: (round(v["ms_per_frame"], 3), round(v.get("speedup_vs_ref_gpu", 0), 1)) for k, v in d.get("combos", {}).items()}))
+    print("orbit", json.dumps(d.get("orbit_2048_strong_scaling"))[:500])
+    r = d["roofline"]; print("roofline", json.dumps({k: r[k] for k in ("achieved", "frac", "bytes_per_ray", "issue", "l2", "traffic")}))
+except Exception as e:
+    print("no bench line", e)
+PY
+timeout 900 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r02z_bench_reference_arm.json 2> gpurun_out/r02z_bench_reference_arm.err; cut -c1-330 gpurun_out/r02z_bench_reference_arm.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02z_launches_bench.csv \
+    python bench.py --steps 5 --warmup 3 --no-baselines > gpurun_out/r02z_ncu_launches_bench.log 2>&1
+timeout 900 python tools/ab_variants.py prev main > gpurun_out/r02z_ab.log 2>&1; cat gpurun_out/r02z_ab.log
+cp gpurun_out/ab.json gpurun_out/r02z_ab.json
+timeout 300 python tools/ncu_targets.py trace5 longestaxis 2>&1 | tail -2
+timeout 300 python tools/ncu_targets.py trace5 original 2>&1 | tail -2
+du -sh gpurun_out
