@@ -90,6 +90,7 @@ struct vrm_scene
 
 	uint8_t* d_dmaFrame = nullptr;    size_t dmaFrameBytes = 0;    // vrm_render into a page-locked buffer, copy-engine form
 	int pinnedDma = 0;                // bands of that form (VRM_PINNED_DMA); 0 = the kernels store into the mapped buffer themselves
+	int traceSort = 1;                // trace_rays: order the rays by origin cell and direction before tracing (VRM_TRACE_SORT=0: caller order)
 	bool wstoreRemote = false;        // A/B: per-warp stores for frames outside this GPU's memory too (VRM_WSTORE_REMOTE)
 	uint8_t* d_localFrame = nullptr;  size_t localFrameBytes = 0;  // frames of a queue-pipeline launch whose destination is not local memory
 	int shadowForm = -1;              // shadow kernel: -1 per-combination default, 0 nested loops, 1 state machine, 2 state machine with lane-level refill (VRM_SHADOW_FORM)
@@ -133,6 +134,9 @@ void vrm_free_async(vrm_scene* s, void* p);
 void vrm_configure_pool(int device);
 size_t vrm_scan_scratch_elems(uint64_t n);  // uint32 elements of scratch an exclusive scan of n elements needs
 void vrm_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st);  // out may alias in
+// the builder's stable LSD radix sort on (32-bit key, 32-bit value) pairs (vrm_build.cu)
+size_t vrm_sort_work_elems(uint64_t n, int keyBits);
+void vrm_sort_pairs_u32(uint32_t*& keys, uint32_t*& vals, uint32_t* keysB, uint32_t* valsB, uint64_t n, int keyBits, uint32_t* work, cudaStream_t st);
 
 // vrm_api.cu: install / remove the access-policy window on the handle's current stream (called by the launch wrappers)
 void vrm_apply_l2_window(vrm_scene* s);

@@ -637,7 +637,50 @@ struct TraceArgs
 	unsigned int* shadowCtl;
 	uint32_t shadowCap;
 	uint32_t skipDead;
+	const uint32_t* order; // null: thread t of the launch traces ray first + t; else ray first + order[t] (rays ordered for coherence, below)
 };
+
+// ---- ray ordering for trace_rays -----------------------------------------------------------------------------------------------------
+// Caller-supplied rays arrive in the caller's order (BASELINE configs[4]: one random direction per pixel): the 32 rays of a warp then
+// walk 32 unrelated paths and a warp instruction serves 6 of its 32 lanes (profiles/r02z_ncu_trace_config5_vcs_longestaxis.json).
+// Rays are independent, so WHICH thread traces which ray is free: a launch first sorts its ray indices by a 26-bit key -- origin region
+// parity (3 bits), cube-map face of the direction (3 bits), Morton code of the two minor direction components over the major one
+// (2 x 10 bits) -- with the builder's radix sort (3 passes), and thread t traces ray order[t]: a warp then holds a small patch of
+// direction space from one neighbourhood, like a tile of primary rays.  Colours, hit records and shadow-queue records carry the ray's
+// own index, so results land where the caller expects them; every ray executes exactly what it always did.
+__device__ __forceinline__ uint32_t spread10(uint32_t v)
+{
+	v &= 0x3FFu;
+	v = (v | (v << 8)) & 0x00FF00FFu;
+	v = (v | (v << 4)) & 0x0F0F0F0Fu;
+	v = (v | (v << 2)) & 0x33333333u;
+	v = (v | (v << 1)) & 0x55555555u;
+	return v;
+}
+
+__global__ void ray_key_kernel(const float* __restrict__ rays, unsigned long long first, uint32_t m, float tx, float ty, float tz, float scale,
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	const float* r = rays + 6 * (first + t);
+	const float o0 = (r[0] - tx) * scale, o1 = (r[1] - ty) * scale, o2 = (r[2] - tz) * scale;
+	const float d0 = r[3], d1 = r[4], d2 = r[5];
+	const float a0 = fabsf(d0), a1 = fabsf(d1), a2 = fabsf(d2);
+	int major = 0;
+	float am = a0, u = d1, v = d2, dm = d0;
+	if (a1 > am) { major = 1; am = a1; u = d0; v = d2; dm = d1; }
+	if (a2 > am) { major = 2; am = a2; u = d0; v = d1; dm = d2; }
+	const float inv = am > 0.0f ? 1.0f / am : 0.0f;
+	// (a sort key, not traversal arithmetic: any value is a valid key, NaN / inf just land in the clamped corners)
+	const uint32_t qu = (uint32_t)fminf(fmaxf((u * inv * 0.5f + 0.5f) * 1023.0f, 0.0f), 1023.0f);
+	const uint32_t qv = (uint32_t)fminf(fmaxf((v * inv * 0.5f + 0.5f) * 1023.0f, 0.0f), 1023.0f);
+	const uint32_t face = (uint32_t)major * 2u + (dm < 0.0f ? 1u : 0u);
+	const uint32_t cell = ((uint32_t)(int)floorf(o0 * 0.015625f) & 1u) | (((uint32_t)(int)floorf(o1 * 0.015625f) & 1u) << 1) | (((uint32_t)(int)floorf(o2 * 0.015625f) & 1u) << 2);
+	keys[t] = (cell << 23) | (face << 20) | (spread10(qu) << 1) | spread10(qv);
+	vals[t] = t;
+}
+constexpr int kRayKeyBits = 26;
 
 // Incoherent rays are latency-bound: occupancy is worth more than a few spilled registers (measured, 1024^3 shells, 8.3 M rays:
 // VCS + original 9.37 ms at 54 registers / 4 CTAs, 8.82 at 48 / 5, 8.31 at 40 / 6; VCS + longest axis 16.77 at 78 / 3, 14.14 at 64 / 4, 14.50 at 48 / 5).
@@ -652,7 +695,9 @@ __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MI
 {
 	// PRIMARY phase of caller-supplied rays (rayMarchVoxelScene[LongestAxis] called per ray); a hit is shaded and its
 	// shadow ray queued for shadow_kernel, exactly as in render_kernel.  Incoherent rays: every lane runs its own loop.
-	const unsigned long long i = a.first + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	const unsigned long long t = a.first + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	const bool live = t < a.n;
+	const unsigned long long i = (live && a.order) ? a.first + __ldg(a.order + (t - a.first)) : t;  // the ray this thread traces
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
@@ -663,7 +708,7 @@ __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MI
 	bool hit = false;
 	ShadowStart ss;
 	ss.hitW[0] = ss.hitW[1] = ss.hitW[2] = 0.0f; ss.regW[0] = ss.regW[1] = ss.regW[2] = 0; ss.lit = 0u; ss.la = 0;
-	if (i < a.n)
+	if (live)
 	{
 		const float o[3] = {__ldg(a.rays + 6 * i), __ldg(a.rays + 6 * i + 1), __ldg(a.rays + 6 * i + 2)};
 		const float d[3] = {__ldg(a.rays + 6 * i + 3), __ldg(a.rays + 6 * i + 4), __ldg(a.rays + 6 * i + 5)};
@@ -1210,7 +1255,7 @@ int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float*
 	vrm_apply_l2_window(s);
 	TraceArgs a;
 	fill_common(a, s, translation, scale);
-	a.rays = d_rays; a.n = n; a.colour = d_colour; a.hits = d_hits;
+	a.rays = d_rays; a.n = n; a.colour = d_colour; a.hits = d_hits; a.order = nullptr;
 	if (s->statsEnabled)
 	{
 		VRM_CUDA(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Stats), s->stream));
@@ -1224,10 +1269,27 @@ int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float*
 		a.first = first;
 		const unsigned grid = (unsigned)((m + 255) / 256);
 		a.n = first + m;
+		// order the launch's rays for coherence (see ray_key_kernel); tiny batches and the lean test kernels take the caller's order
+		void* sortBuf = nullptr;
+		a.order = nullptr;
+		if (s->traceSort && m >= 1024 && s->renderMode != 3)
+		{
+			const size_t mPad = (size_t)((m + 63) & ~63ull), workElems = vrm_sort_work_elems(m, kRayKeyBits);
+			if (vrm_alloc_async(s, &sortBuf, (4 * mPad + workElems) * sizeof(uint32_t)) == cudaSuccess)
+			{
+				uint32_t* keys = static_cast<uint32_t*>(sortBuf);
+				uint32_t* vals = keys + mPad; uint32_t* keysB = vals + mPad; uint32_t* valsB = keysB + mPad; uint32_t* work = valsB + mPad;
+				ray_key_kernel<<<grid, 256, 0, s->stream>>>(d_rays, first, (uint32_t)m, translation[0], translation[1], translation[2], static_cast<float>(scale), keys, vals);
+				vrm_sort_pairs_u32(keys, vals, keysB, valsB, m, kRayKeyBits, work, s->stream);
+				a.order = vals;
+			}
+			else { cudaGetLastError(); sortBuf = nullptr; }  // no scratch: caller order
+		}
 		if (hash && orig) launch_trace_t<kStorageHash, kAlgoOriginal>(s, a, grid);
 		else if (hash) launch_trace_t<kStorageHash, kAlgoLongestAxis>(s, a, grid);
 		else if (orig) launch_trace_t<kStorageVcs, kAlgoOriginal>(s, a, grid);
 		else launch_trace_t<kStorageVcs, kAlgoLongestAxis>(s, a, grid);
+		if (sortBuf) vrm_free_async(s, sortBuf);
 		VRM_CUDA(s, cudaGetLastError());
 	}
 	return VRM_OK;
