@@ -185,6 +185,7 @@ int vrm_scene_create(int device, vrm_scene** out)
 	if (const char* form = getenv("VRM_SHADOW_FORM")) { const int f = atoi(form); if (f >= 0 && f <= 2) s->shadowForm = f; }
 	if (const char* lp = getenv("VRM_L2_PERSIST")) s->l2Persist = atoi(lp) != 0;
 	if (const char* ts = getenv("VRM_TRACE_SORT")) s->traceSort = atoi(ts);
+	if (const char* tf = getenv("VRM_TRACE_FUSED")) s->traceFused = atoi(tf);
 	if (const char* pd = getenv("VRM_PINNED_DMA")) s->pinnedDma = atoi(pd);
 	if (const char* ws = getenv("VRM_WSTORE_REMOTE")) s->wstoreRemote = atoi(ws) != 0;
 	if (const char* bb = getenv("VRM_VIEW_BATCH_BYTES")) { long long v = atoll(bb); if (v > 0) s->viewBatchBytes = (size_t)v; }

@@ -745,6 +745,44 @@ __global__ void __launch_bounds__(256, ALGO == kAlgoOriginal ? VRM_TRACE_ORIG_MI
 	flush_stats<STATS>(c, a.stats);
 }
 
+// Ordered rays (ray_key_kernel) are coherent like the primary rays of a tile, so VCS + longest axis traces them the way render_kernel
+// does: the warp-cooperative state machine with its fast blocks, primary and shadow ray in one kernel behind the hit barrier.
+constexpr int kTraceFusedThreads = 128;
+template <int ST, int ALGO, bool STATS>
+__global__ void __launch_bounds__(kTraceFusedThreads, VRM_FUSED_CTAS > 0 ? VRM_FUSED_CTAS : 8) trace_fused_kernel(const TraceArgs a)
+{
+	const unsigned long long t = a.first + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	const bool live = t < a.n;
+	const unsigned long long i = (live && a.order) ? a.first + __ldg(a.order + (t - a.first)) : t;
+	RayCtx<ST, STATS> c;
+	c.sv = a.sv;
+	c.light = a.light;
+	c.lw = a.lw;
+	c.hitOut = nullptr;
+	c.translation[0] = a.translation[0]; c.translation[1] = a.translation[1]; c.translation[2] = a.translation[2];
+	c.reset();
+	c.deferQueue = a.defer;
+	c.skipDead = a.skipDead;
+	float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
+	if (live)
+	{
+		for (int k = 0; k < 3; k++) { o[k] = __ldg(a.rays + 6 * i + k); d[k] = __ldg(a.rays + 6 * i + 3 + k); }
+		if (a.hits)
+		{
+			c.hitOut = a.hits + 4 * i;
+			*reinterpret_cast<int4*>(c.hitOut) = make_int4(0, 0, 0, 0);
+		}
+	}
+	int slot;
+	const uint32_t colour = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, live, o, d, a.scale, slot);
+	if (live)
+	{
+		if (slot >= 0) park_output<FlatRay<ST, ALGO, STATS>>(a.defer, slot, a.colour + i, 1u);
+		a.colour[i] = colour;
+	}
+	flush_stats<STATS>(c, a.stats);
+}
+
 
 // ---- lean state machine (vrm_lean.cuh) ------------------------------------------------------------------------------------------
 // Same tile mapping and staged stores as render_kernel; per-ray constants in shared memory ([vector][thread]); rays that need a
@@ -1135,6 +1173,19 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 		trace_lean_kernel<ST, ALGO><<<(unsigned)((a.n + kLeanTraceThreads - 1) / kLeanTraceThreads), kLeanTraceThreads, 0, s->stream>>>(a);
 		resume_lean_kernel<ST, ALGO, false, TraceArgs><<<(unsigned)s->numSms, kResumeLeanThreads, 0, s->stream>>>(a, a.n);
 		return;
+	}
+	if constexpr (ST == kStorageVcs && ALGO != kAlgoOriginal)
+	{
+		if (mode == 2 && a.order && s->traceFused)
+		{
+			a.defer = prepare_defer_queue<ST, ALGO>(s);
+			a.skipDead = s->statsMode == 1 ? 0u : 1u;
+			const unsigned g = (unsigned)((a.n - a.first + kTraceFusedThreads - 1) / kTraceFusedThreads);
+			if (s->statsEnabled) trace_fused_kernel<ST, ALGO, true><<<g, kTraceFusedThreads, 0, s->stream>>>(a);
+			else trace_fused_kernel<ST, ALGO, false><<<g, kTraceFusedThreads, 0, s->stream>>>(a);
+			launch_resume<ST, ALGO>(s, a);
+			return;
+		}
 	}
 	if (prepare_shadow_queue(s, (size_t)grid * 256, a) != VRM_OK) return;
 	uint32_t* colour = a.colour + a.first;
