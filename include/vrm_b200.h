@@ -157,7 +157,9 @@ int vrm_render_views(vrm_scene* scene, const float* cameras, uint32_t n_views, c
                      int algorithm, uint32_t width, uint32_t height, uint8_t* rgb_out, float* total_ms);
 
 /* Arbitrary world rays: rays = n x 6 floats (origin xyz, direction xyz).  colour_out = n x uint32, the value the
- * reference's rayMarchVoxelScene[LongestAxis] returns (0 = background); hits_out nullable as above. */
+ * reference's rayMarchVoxelScene[LongestAxis] returns (0 = background); hits_out nullable as above.  Outputs are in the
+ * caller's ray order; the rays themselves are traced in an order chosen for coherence (sorted by origin cell and direction,
+ * VRM_TRACE_SORT=0 disables it) -- rays are independent, so results do not depend on it. */
 int vrm_trace_rays(vrm_scene* scene, const float* rays, uint64_t n, const float translation[3], uint32_t scale,
                    int algorithm, uint32_t* colour_out, int32_t* hits_out, float* kernel_ms);
 int vrm_trace_rays_device(vrm_scene* scene, const float* d_rays, uint64_t n, const float translation[3],
