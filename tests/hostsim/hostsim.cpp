@@ -593,3 +593,92 @@ extern "C" int sim_warp_profile(void* h, const float* cam, const float* tr, uint
 	memcpy(hist, H0.data(), 512 * 8); memcpy(lanes, L0.data(), 512 * 9 * 8); memcpy(totals, T, 32);
 	return 0;
 }
+
+
+// Development aid (tools/warp_profile.py --regroup): what would ABANDON + RE-TRACE buy on a frame with long-tailed tiles?  Phase 1: as
+// sim_warp_profile, but once a tile has run `budget` passes and at most `maxLanes` lanes are still marching, those lanes are dropped and
+// their pixels appended to a list (the lanes waiting with a hit go on).  Phase 2: the listed pixels are traced from scratch, 32 consecutive
+// list entries per warp.  out: {tiles, passes phase 1, passes without regrouping, listed pixels, passes phase 2, lane-passes phase 2}
+extern "C" int sim_regroup_profile(void* h, const float* cam, const float* tr, uint32_t scale, uint32_t W, uint32_t H, uint32_t tileStride,
+	uint32_t budget, uint32_t maxLanes, uint64_t* out, int nThreads)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage != kStorageVcs) return 1;
+	using Ray = FlatRay<kStorageVcs, kAlgoLongestAxis, false>;
+	const uint32_t tilesX = (W + 7) / 8, tilesY = (H + 3) / 4;
+	uint64_t T[6] = {0, 0, 0, 0, 0, 0};
+	std::vector<uint32_t> list;
+	auto run_warp = [&](RayCtx<kStorageVcs, false>& c, Ray* ray, uint32_t budgetHere, uint32_t lanesHere, const uint32_t* pix, std::vector<uint32_t>* parked, uint64_t& passes, uint64_t& lanePasses) {
+		uint32_t n = 0;
+		for (;;)
+		{
+			int marching = 0; bool anyHit = false;
+			for (int l = 0; l < 32; l++) { if (ray[l].st <= kStHead) marching++; if (ray[l].st == kStHit) anyHit = true; }
+			if (marching)
+			{
+				if (parked && n >= budgetHere && (uint32_t)marching <= lanesHere)
+				{
+					for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) { parked->push_back(pix[l]); ray[l].st = kStDone; }
+					continue;
+				}
+				n++; passes++;
+				for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) { ray[l].template step_marching<kPpOff>(c); lanePasses++; }
+				continue;
+			}
+			if (!anyHit) break;
+			for (int l = 0; l < 32; l++) if (ray[l].st == kStHit) ray[l].do_hit(c);
+		}
+	};
+	#pragma omp parallel num_threads(nThreads)
+	{
+		uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+		std::vector<uint32_t> mine;
+		RayCtx<kStorageVcs, false> c;
+		c.sv = s->view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = nullptr;
+		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
+		c.reset(); c.skipDead = 1u;
+		#pragma omp for schedule(dynamic, 1)
+		for (int64_t ty = 0; ty < (int64_t)tilesY; ty += tileStride)
+			for (uint32_t tx = 0; tx < tilesX; tx += tileStride)
+				for (int variant = 0; variant < 2; variant++)
+				{
+					Ray ray[32]; uint32_t pix[32];
+					for (int l = 0; l < 32; l++)
+					{
+						const uint32_t x = tx * 8 + (l & 7), y = (uint32_t)ty * 4 + (l >> 3);
+						pix[l] = y * W + x;
+						ray[l].st = kStDone; ray[l].result = 0;
+						if (x < W && y < H) { float o[3], d[3]; primary_ray_flat(cam, x, y, W, H, 1.0f / (float)W, 1.0f / (float)H, o, d); ray[l].start_primary(c, o, d, (float)scale); }
+					}
+					uint64_t lp = 0;
+					if (variant == 0) { t[0]++; run_warp(c, ray, budget, maxLanes, pix, &mine, t[1], lp); }
+					else run_warp(c, ray, 0, 0, pix, nullptr, t[2], lp);
+				}
+		#pragma omp critical
+		{
+			for (int i = 0; i < 6; i++) T[i] += t[i];
+			list.insert(list.end(), mine.begin(), mine.end());
+		}
+	}
+	std::sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) {  // tile order, as warps would append them
+		const uint32_t ax = a % W, ay = a / W, bx = b % W, by = b / W;
+		const uint64_t ka = ((uint64_t)(ay / 4) * tilesX + ax / 8) * 32 + (ay % 4) * 8 + ax % 8, kb = ((uint64_t)(by / 4) * tilesX + bx / 8) * 32 + (by % 4) * 8 + bx % 8;
+		return ka < kb; });
+	T[3] = list.size();
+	RayCtx<kStorageVcs, false> c;
+	c.sv = s->view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = nullptr;
+	c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
+	c.reset(); c.skipDead = 1u;
+	for (size_t b = 0; b < list.size(); b += 32)
+	{
+		Ray ray[32]; uint32_t pix[32];
+		for (int l = 0; l < 32; l++)
+		{
+			ray[l].st = kStDone; ray[l].result = 0; pix[l] = 0;
+			if (b + l < list.size()) { const uint32_t x = list[b + l] % W, y = list[b + l] / W; float o[3], d[3]; primary_ray_flat(cam, x, y, W, H, 1.0f / (float)W, 1.0f / (float)H, o, d); ray[l].start_primary(c, o, d, (float)scale); }
+		}
+		run_warp(c, ray, 0, 0, pix, nullptr, T[4], T[5]);
+	}
+	memcpy(out, T, sizeof(T));
+	return 0;
+}

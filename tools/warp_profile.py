@@ -25,10 +25,15 @@ def main():
     ap.add_argument("--stride", type=int, default=4)
     ap.add_argument("--view", type=int, default=0)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
+    ap.add_argument("--regroup", default="", help="budget:maxLanes[,budget:maxLanes...]: simulate abandon + re-trace of long-tailed tiles (sim_regroup_profile)")
+    ap.add_argument("--scene", default="terrain", choices=["terrain", "shells2048"], help="shells2048: BASELINE configs[3], one 1080p view of its orbit")
     a = ap.parse_args()
     lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
     lib.sim_scene_create.restype = ctypes.c_void_p
-    xyz, rgb = scenes.terrain(a.size, bench.SCENE_SEED)
+    if a.scene == "terrain":
+        xyz, rgb = scenes.terrain(a.size, bench.SCENE_SEED)
+    else:
+        xyz, rgb = scenes.sparse_shells(2048, 64, seed=7, fill_pct=35)
     h = ctypes.c_void_p(lib.sim_scene_create())
     xyz = np.ascontiguousarray(xyz, np.int32); rgb = np.ascontiguousarray(rgb, np.uint32)
     lib.sim_scene_add_voxels(h, xyz.ctypes.data_as(ctypes.c_void_p), rgb.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(rgb)))
@@ -36,11 +41,27 @@ def main():
     light = [np.array(v, np.float32) for v in ((0.57735026, 0.57735026, 0.57735026), (1, 1, 1), (10, 10, -10))]
     d = np.zeros(3, np.float32)
     lib.sim_make_unit_vector(np.array([1.0, 1.0, 1.0], np.float32).ctypes.data_as(ctypes.c_void_p), d.ctypes.data_as(ctypes.c_void_p))
-    cam = bench.orbit_camera(api, a.view)
+    W, H = bench.WIDTH, bench.HEIGHT
+    if a.scene == "terrain":
+        cam = bench.orbit_camera(api, a.view)
+    else:
+        W, H = 1920, 1080
+        cam = bench.orbit_views_2048(api, W, H)[a.view]
     camv = np.ascontiguousarray(cam.data, np.float32)
     tr = np.zeros(3, np.float32)
+    if a.regroup:
+        for spec in a.regroup.split(","):
+            budget, lanes_max = (int(v) for v in spec.split(":"))
+            out = np.zeros(6, np.uint64)
+            rc = lib.sim_regroup_profile(h, camv.ctypes.data_as(ctypes.c_void_p), tr.ctypes.data_as(ctypes.c_void_p), 1, W, H, a.stride, budget, lanes_max,
+                                         out.ctypes.data_as(ctypes.c_void_p), a.threads)
+            assert rc == 0
+            tiles, p1, p0, listed, p2, lp2 = (int(v) for v in out)
+            print(f"budget {budget:4d} lanes<= {lanes_max:2d}: passes/tile {p0 / tiles:7.2f} -> phase 1 {p1 / tiles:7.2f} + phase 2 {p2 / tiles:6.2f} = {(p1 + p2) / tiles:7.2f} "
+                  f"({100 * (p1 + p2) / p0:5.1f} %), re-traced pixels {100 * listed / (tiles * 32):5.1f} %, phase-2 lanes/pass {lp2 / max(p2, 1):5.1f}")
+        return
     hist = np.zeros(512, np.uint64); lanes = np.zeros((512, 9), np.uint64); tot = np.zeros(4, np.uint64)
-    rc = lib.sim_warp_profile(h, camv.ctypes.data_as(ctypes.c_void_p), tr.ctypes.data_as(ctypes.c_void_p), 1, bench.WIDTH, bench.HEIGHT, a.stride,
+    rc = lib.sim_warp_profile(h, camv.ctypes.data_as(ctypes.c_void_p), tr.ctypes.data_as(ctypes.c_void_p), 1, W, H, a.stride,
                               hist.ctypes.data_as(ctypes.c_void_p), lanes.ctypes.data_as(ctypes.c_void_p), tot.ctypes.data_as(ctypes.c_void_p), a.threads)
     assert rc == 0
     tiles, passes, shade, lanepasses = (int(v) for v in tot)
