@@ -682,3 +682,68 @@ extern "C" int sim_regroup_profile(void* h, const float* cam, const float* tr, u
 	memcpy(out, T, sizeof(T));
 	return 0;
 }
+
+
+// Development aid (tools/warp_profile.py --compact N): what would packing the SHADOW rays of the N tiles of a CTA into full warps buy (the primary
+// phase stays per tile; behind a CTA barrier the live shadow rays of the CTA's tiles are packed 32 per warp in tile order)?
+// out: {CTAs, primary passes, shadow passes per tile (today), shadow passes packed, shadow lane-passes, shadow rays, worst-tile primary passes summed over CTAs}
+extern "C" int sim_cta_compact_profile(void* h, const float* cam, const float* tr, uint32_t scale, uint32_t W, uint32_t H, uint32_t ctaStride, uint32_t tilesPerCta,
+	uint64_t* out, int nThreads)
+{
+	SimScene* s = static_cast<SimScene*>(h);
+	if (s->storage != kStorageVcs || tilesPerCta == 0 || tilesPerCta > 16) return 1;
+	using Ray = FlatRay<kStorageVcs, kAlgoLongestAxis, false>;
+	const uint32_t ctasX = (W + 8 * tilesPerCta - 1) / (8 * tilesPerCta), ctasY = (H + 3) / 4;
+	uint64_t T[7] = {0, 0, 0, 0, 0, 0, 0};
+	auto run = [](RayCtx<kStorageVcs, false>& c, Ray* ray, uint64_t& passes, uint64_t& lanePasses) {
+		uint64_t n = 0;
+		for (;;)
+		{
+			bool marching = false;
+			for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) marching = true;
+			if (!marching) break;
+			passes++; n++;
+			for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) { ray[l].template step_marching<kPpOff>(c); lanePasses++; }
+		}
+		return n;
+	};
+	#pragma omp parallel num_threads(nThreads)
+	{
+		uint64_t t[7] = {0, 0, 0, 0, 0, 0, 0};
+		RayCtx<kStorageVcs, false> c;
+		c.sv = s->view(); c.light = gLight; c.lw = make_light_walk(gLight); c.hitOut = nullptr;
+		c.translation[0] = tr[0]; c.translation[1] = tr[1]; c.translation[2] = tr[2];
+		c.reset(); c.skipDead = 1u;
+		std::vector<Ray> tiles(32 * 16), packed;
+		#pragma omp for schedule(dynamic, 1)
+		for (int64_t cy = 0; cy < (int64_t)ctasY; cy += ctaStride)
+			for (uint32_t cx = 0; cx < ctasX; cx += ctaStride)
+			{
+				t[0]++;
+				uint64_t dummy = 0, worst = 0;
+				packed.clear();
+				for (uint32_t k = 0; k < tilesPerCta; k++)
+				{
+					Ray* ray = &tiles[32 * k];
+					for (int l = 0; l < 32; l++)
+					{
+						const uint32_t x = (cx * tilesPerCta + k) * 8 + (l & 7), y = (uint32_t)cy * 4 + (l >> 3);
+						ray[l].st = kStDone; ray[l].result = 0;
+						if (x < W && y < H) { float o[3], d[3]; primary_ray_flat(cam, x, y, W, H, 1.0f / (float)W, 1.0f / (float)H, o, d); ray[l].start_primary(c, o, d, (float)scale); }
+					}
+					const uint64_t n = run(c, ray, t[1], dummy);
+					if (n > worst) worst = n;
+					for (int l = 0; l < 32; l++) if (ray[l].st == kStHit) ray[l].do_hit(c);
+					for (int l = 0; l < 32; l++) if (ray[l].st <= kStHead) { packed.push_back(ray[l]); t[5]++; }
+					run(c, ray, t[2], t[4]);
+				}
+				t[6] += worst;
+				while (packed.size() % 32) { Ray r; r.st = kStDone; r.result = 0; packed.push_back(r); }
+				for (size_t b = 0; b < packed.size(); b += 32) run(c, &packed[b], t[3], dummy);
+			}
+		#pragma omp critical
+		for (int i = 0; i < 7; i++) T[i] += t[i];
+	}
+	memcpy(out, T, sizeof(T));
+	return 0;
+}
