@@ -17,6 +17,10 @@
 // Reference file:line citations are relative to /root/reference/VoxelRaymarcher/src.
 #pragma once
 
+#ifndef VRM_SMEM_MASK
+#define VRM_SMEM_MASK 0  // 1 (with VRM_VCS_FUSED_EXIST=0): per-warp shared-memory copy of the current region's cluster mask in the fused render kernel (measured, off)
+#endif
+
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
@@ -384,10 +388,19 @@ template <int ST, bool STATS> struct RayCtx
 	// 1: a hit whose shaded colour is already black starts no shadow ray (Renderer.cuh:314-315: 0 * !isInShadow = 0 whatever the shadow
 	// ray finds).  0 (host harness, reference-comparable event counters): every hit's shadow ray is traced, as the reference does.
 	uint32_t skipDead;
+#if VRM_SMEM_MASK
+	// A/B form (north-star "shared-memory staging of cluster headers"): the warp's copy of ONE region's 512-bit
+	// cluster-exists mask in shared memory and the region it belongs to (warp-uniform; -1 = none).  Filled by march_scene_flat_warp.
+	uint32_t* smMask;
+	int32_t smRi;
+#endif
 	Stats st;
 
 	VRM_HD void reset()
 	{
+#if VRM_SMEM_MASK
+		smMask = nullptr; smRi = -1;
+#endif
 		hit[0] = hit[1] = hit[2] = hit[3] = 0;
 		deferQueue = nullptr;
 		skipDead = 0u;

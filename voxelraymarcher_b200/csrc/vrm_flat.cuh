@@ -451,7 +451,13 @@ struct FlatRay
 			if (!e) return false;
 #else
 			const uint32_t cid = cc >> 9;
+#if VRM_SMEM_MASK && defined(__CUDA_ARCH__)
+			// the warp's staged copy when this lane is in the staged region, else the mask in global memory
+			const uint32_t mw = (c.smMask && ri == c.smRi) ? c.smMask[cid >> 5] : ldg(c.sv.clusterMask + ((uint32_t)ri * 16u + (cid >> 5)));
+			const bool e = (mw >> (cid & 31u)) & 1u;
+#else
 			const bool e = (ldg(c.sv.clusterMask + ((uint32_t)ri * 16u + (cid >> 5))) >> (cid & 31u)) & 1u;
+#endif
 			if (STATS) { c.st.nExist++; if (!e) c.st.nExistFalse++; }
 			if (!e) return false;
 			const uint2 h = ldg(c.sv.headers + ((uint32_t)ri * 8192u + (cc >> 5)));
@@ -952,6 +958,24 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 		bool generic = false;  // warp-uniform: a lane's step did not qualify for the fast path it was offered
 		for (;;)
 		{
+#if VRM_SMEM_MASK
+			if (c.smMask)
+			{
+				// stage the cluster mask of the region the first marching lane is in (the lanes of a tile mostly share it)
+				const unsigned inRegion = __ballot_sync(0xFFFFFFFFu, ray.st <= kStHead && ray.ri >= 0);
+				if (inRegion != 0u)
+				{
+					const int32_t want = __shfl_sync(0xFFFFFFFFu, ray.ri, __ffs(inRegion) - 1);
+					if (want != c.smRi)
+					{
+						__syncwarp();
+						if ((threadIdx.x & 31u) < 16u) c.smMask[threadIdx.x & 31u] = ldg(c.sv.clusterMask + ((uint32_t)want * 16u + (threadIdx.x & 31u)));
+						c.smRi = want;
+						__syncwarp();
+					}
+				}
+			}
+#endif
 			// what the warp's marching lanes (kStMain, kStRegion, kStHead) are about to do: 1 a cluster jump, 2 a null-region skip, 4 anything else
 			const bool isJump = ray.st == kAdvJump, isNull = ray.st == kStRegion && ray.ri == -1;
 #if VRM_FAST_LA

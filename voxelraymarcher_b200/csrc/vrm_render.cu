@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(kRenderThreads, (FORM == 2 && VRM_FUSED_CTAS >
 		if constexpr (FORM == 2)
 		{
 			c.skipDead = a.skipDead;
+#if VRM_SMEM_MASK
+			__shared__ uint32_t stagedMask[kRenderThreads / 32][16];
+			c.smMask = stagedMask[warp];
+#endif
 			// both phases here: lanes that hit wait at the hit barrier, the tile then shades and walks its shadow rays together
 			int slot;
 			color = march_scene_flat_warp<ST, ALGO, STATS, kPpDefer>(c, inside, o, d, a.scale, slot);
