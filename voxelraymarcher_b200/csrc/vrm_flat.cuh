@@ -94,6 +94,12 @@ constexpr int kPpOff = 0, kPpDefer = 1, kPpInline = 2;
 #ifndef VRM_FAST_LA
 #define VRM_FAST_LA 7      // a third warp-uniform block: longest-axis stepping (FlatRay::fast_la); A/B bits: 2 = without the stored-region entry, 4 = without the inner loop
 #endif
+#ifndef VRM_CC_MUL
+#define VRM_CC_MUL 1       // 1: FlatRay::sh holds 1 << shift and the storage codes are multiply-add chains instead of shifts + ORs (A/B)
+#endif
+#ifndef VRM_CLS_LUT
+#define VRM_CLS_LUT 1      // 1: the class a lane votes with comes from a nibble table indexed by the state word (A/B)
+#endif
 #ifndef VRM_FAST_ENTER
 #define VRM_FAST_ENTER 0   // 1: fast_jump / fast_nullskip run a stored region's entry block in the pass that changed region (A/B: 1.338 vs 1.332 ms, off)
 #endif
@@ -216,6 +222,9 @@ struct FlatRay
 		for (int i = 0; i < 3; i++)
 		{
 			sh[i] = ST == kStorageHash ? (uint32_t)(kHashKeyBits * (2 - a[i])) : (uint32_t)(6 - 3 * a[i]);
+#if VRM_CC_MUL
+			sh[i] = 1u << sh[i];  // kept as the multiplier: the three fields are disjoint, so the code is one multiply-add chain
+#endif
 			rs[i] = a[i] == 0 ? 1u : (a[i] == 1 ? D : D * D);
 		}
 	}
@@ -421,7 +430,11 @@ struct FlatRay
 		col = kEmpty;
 		if constexpr (ST == kStorageHash)
 		{
+#if VRM_CC_MUL
+			const uint32_t key = (uint32_t)c0 * sh[0] + (uint32_t)c1 * sh[1] + (uint32_t)c2 * sh[2];
+#else
 			const uint32_t key = ((uint32_t)c0 << sh[0]) | ((uint32_t)c1 << sh[1]) | ((uint32_t)c2 << sh[2]);
+#endif
 #if VRM_HASH_CLUSTER_FILTER
 			if (hash_cluster_occupied(c.sv.clusterMask, r.ri, key))  // negative filter, see lookup_voxel (vrm_core.cuh)
 #endif
@@ -441,7 +454,11 @@ struct FlatRay
 			// (v & 7) | (v >> 3) << 9 = (v * 65) & 0x1E07, shifted to its axis' place.  (Bit 12 of the mask only matters for v = 64, the
 			// reference's undefined corner -- a ray rebased onto the far face of a region: it makes this form alias the coordinate
 			// into the neighbouring cluster id exactly like the nested form and the C oracle do.)
+#if VRM_CC_MUL
+			const uint32_t cc = (((uint32_t)c0 * 65u) & 0x1E07u) * sh[0] + (((uint32_t)c1 * 65u) & 0x1E07u) * sh[1] + (((uint32_t)c2 * 65u) & 0x1E07u) * sh[2];
+#else
 			const uint32_t cc = ((((uint32_t)c0 * 65u) & 0x1E07u) << sh[0]) | ((((uint32_t)c1 * 65u) & 0x1E07u) << sh[1]) | ((((uint32_t)c2 * 65u) & 0x1E07u) << sh[2]);
+#endif
 			// header word index inside the region = cid * 16 + code / 32 = cc >> 5; bit = code % 32 = cc % 32
 #if VRM_VCS_FUSED_EXIST
 			// ONE 8-byte load answers both questions: the word's .y carries the cluster-exists flag (vrm_build.cu)
@@ -981,7 +998,15 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 #if VRM_FAST_LA
 			// 8: longest-axis stepping (stored-region entry, loop head, a voxel test of the current iteration)
 			const bool isLa = ray.st == kStHead || ray.st == kAdvNone || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
+#if VRM_CLS_LUT && (VRM_FAST_LA & 2)
+			// the class is a function of the state word alone (one nibble per state: kAdvNone 8, kAdvNext 4, kAdvCluster 4, kAdvJump 1,
+			// kAdvRegion 4, kStRegion 4, kStHead 8, the rest 0) except for the null-region entry
+			const unsigned nib = (unsigned)ray.st > 7u ? 0u : ((0x08441448u >> ((unsigned)ray.st * 4u)) & 15u);
+			const unsigned cls = isNull ? 2u : nib;
+			(void)isJump; (void)isLa;
+#else
 			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : (isLa ? 8u : 4u))) : 0u;
+#endif
 #else
 			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : 4u)) : 0u;
 #endif
