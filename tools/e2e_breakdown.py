@@ -24,6 +24,7 @@ FORMS = {
     "dma4": {"VRM_PINNED_DMA": "4"},
     "dma8": {"VRM_PINNED_DMA": "8"},
     "wstore": {"VRM_WSTORE_REMOTE": "1"},
+    "nobulk": {"VRM_BULK_STORE": "0"},
 }
 
 
@@ -41,7 +42,7 @@ def main():
     frame = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
     cams = [bench.orbit_camera(api, bench.view_of(i, 0, 1)) for i in range(a.iters + 3)]
     for name in a.forms.split(","):
-        for k in ("VRM_PINNED_DMA", "VRM_WSTORE_REMOTE"):
+        for k in ("VRM_PINNED_DMA", "VRM_WSTORE_REMOTE", "VRM_BULK_STORE"):
             os.environ.pop(k, None)
         os.environ.update(FORMS[name])
         s = api.VoxelScene(0)

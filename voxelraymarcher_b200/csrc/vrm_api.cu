@@ -188,6 +188,7 @@ int vrm_scene_create(int device, vrm_scene** out)
 	if (const char* tf = getenv("VRM_TRACE_FUSED")) s->traceFused = atoi(tf);
 	if (const char* pd = getenv("VRM_PINNED_DMA")) s->pinnedDma = atoi(pd);
 	if (const char* ws = getenv("VRM_WSTORE_REMOTE")) s->wstoreRemote = atoi(ws) != 0;
+	if (const char* bs = getenv("VRM_BULK_STORE")) s->bulkStore = atoi(bs) != 0;
 	if (const char* bb = getenv("VRM_VIEW_BATCH_BYTES")) { long long v = atoll(bb); if (v > 0) s->viewBatchBytes = (size_t)v; }
 	if (e != cudaSuccess) { vrm_scene_destroy(s); cudaGetLastError(); return VRM_ERR_CUDA; }
 	s->stream = s->ownStream;

@@ -92,6 +92,7 @@ struct vrm_scene
 	int pinnedDma = 0;                // bands of that form (VRM_PINNED_DMA); 0 = the kernels store into the mapped buffer themselves
 	int traceSort = 1;                // trace_rays: order the rays by origin cell and direction before tracing (VRM_TRACE_SORT=0: caller order)
 	int traceFused = 1;               // ordered rays, VCS + longest axis: warp-cooperative fused kernel instead of primary + shadow-ray queue (VRM_TRACE_FUSED=0)
+	bool bulkStore = true;            // frames outside this GPU's memory: CTA-staged rows leave as bulk async copies (cp.async.bulk), VRM_BULK_STORE=0: ordinary stores
 	bool wstoreRemote = false;        // A/B: per-warp stores for frames outside this GPU's memory too (VRM_WSTORE_REMOTE)
 	uint8_t* d_localFrame = nullptr;  size_t localFrameBytes = 0;  // frames of a queue-pipeline launch whose destination is not local memory
 	int shadowForm = -1;              // shadow kernel: -1 per-combination default, 0 nested loops, 1 state machine, 2 state machine with lane-level refill (VRM_SHADOW_FORM)

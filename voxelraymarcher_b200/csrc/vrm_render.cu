@@ -68,6 +68,7 @@ struct RenderArgs
 	float invW, invH;      // RN(1 / W), RN(1 / H) (host): exact division by a constant in primary_ray_flat
 	uint32_t rgbLocal;     // host side only: the frame `rgb` points into this GPU's own memory (selects the per-warp store kernels)
 	uint32_t rowWordsOk;   // 1 when every 32-pixel row segment starts on a 4-byte boundary (W * 3 % 4 == 0 and an aligned base)
+	uint32_t rowBulkOk;    // 1 when every such segment also starts on a 16-byte boundary and the frame is not in this GPU's memory: the CTA-staged rows leave as bulk async copies
 	uint32_t yBase, yEnd;  // rows rendered by this launch (a band of the frame: vrm_render overlaps the D2H copy of band k with band k+1)
 	uint8_t* rgb;       // nViews x H x W x 3
 	int32_t* hits;      // nullable, nViews x H x W x 4
@@ -205,6 +206,21 @@ __global__ void __launch_bounds__(kResumeThreads) resume_kernel(const ResumeArgs
 	}
 }
 
+// Bulk asynchronous copy shared -> global (the TMA unit's non-tensor form).  A CTA whose last instruction is an ordinary store into
+// page-locked host memory or a peer GPU keeps its slot on the SM until PCIe / NVLink has acknowledged the store; a bulk copy is handed
+// to the copy unit, and the CTA only waits until its shared memory has been READ (cp.async.bulk.wait_group.read) before it leaves.
+// dst and src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_store_row(void* dst, const void* src, uint32_t bytes)
+{
+	const uint32_t s = (uint32_t)__cvta_generic_to_shared(src);
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_release()
+{
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // FORM 0: nested loops, primary rays only (shadow rays go to the queue); 1: state machine, primary rays only; 2: state machine with the
 // shadow ray in the kernel behind a hit barrier (march_scene_flat_warp) -- the default for VCS + longest axis, see launch_render_t
 // WSTORE: every warp writes its own 8x4 tile (four 24-byte row segments) and leaves -- no CTA barrier, so a warp that finishes early does
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(kRenderThreads, (FORM == 2 && VRM_FUSED_CTAS >
 	// The CTA's 32x4 pixels are staged in shared memory and written as 4 rows of 96 contiguous bytes (24 words per row,
 	// one STG.32 per thread) instead of three scattered byte stores per pixel (Renderer.cuh:1027-1030); this is also what makes
 	// writing the frame straight into pinned host memory (vrm_render) efficient.
-	__shared__ uint32_t staged[kBlockH][kBlockW * 3 / 4];
+	__shared__ __align__(16) uint32_t staged[kBlockH][kBlockW * 3 / 4];
 	RayCtx<ST, STATS> c;
 	c.sv = a.sv;
 	c.light = a.light;
@@ -336,12 +352,26 @@ __global__ void __launch_bounds__(kRenderThreads, (FORM == 2 && VRM_FUSED_CTAS >
 	{
 		uint8_t* sb = reinterpret_cast<uint8_t*>(&staged[ly][0]) + lx * 3;
 		sb[0] = (uint8_t)(color >> 16); sb[1] = (uint8_t)((color >> 8) & 0xFF); sb[2] = (uint8_t)(color & 0xFF);
+		if (a.rowBulkOk)
+		{
+			// remote frame: one bulk async copy per 96-byte row segment, issued by the first kBlockH threads
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			__syncthreads();
+			if (threadIdx.x < kBlockH)
+			{
+				bulk_store_row(a.rgb + ((size_t)blockIdx.z * a.rgbViewPixels + (size_t)(y0 + threadIdx.x) * a.W + x0) * 3, &staged[threadIdx.x][0], kBlockW * 3);
+				bulk_store_commit_and_release();
+			}
+		}
+		else
+		{
 		__syncthreads();
 		if (threadIdx.x < kBlockH * (kBlockW * 3 / 4))
 		{
 			const uint32_t row = threadIdx.x / (kBlockW * 3 / 4), w = threadIdx.x % (kBlockW * 3 / 4);
 			uint32_t* dst = reinterpret_cast<uint32_t*>(a.rgb + ((size_t)blockIdx.z * a.rgbViewPixels + (size_t)(y0 + row) * a.W + x0) * 3);
 			dst[w] = staged[row][w];
+		}
 		}
 	}
 	else if (inside)
@@ -1254,6 +1284,9 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 		const bool local = cudaPointerGetAttributes(&at, d_rgb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == s->device;
 		cudaGetLastError();
 		a.rgbLocal = (local || s->wstoreRemote) ? 1u : 0u;
+		// frames outside this GPU's memory leave the CTA as bulk async copies when every 96-byte row segment is 16-byte aligned
+		a.rowBulkOk = (!local && s->bulkStore && a.rowWordsOk && (kBlockW * 3) % 16 == 0 && ((size_t)W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_rgb) & 15u) == 0 &&
+		               (((size_t)W * H * 3 * (viewStride ? viewStride : 1u)) % 16 == 0 || nViews == 1)) ? 1u : 0u;
 		viaLocal = !local && (mode == 1 || mode == 4) && s->light.useShadows;
 	}
 	const size_t frameBytes = (size_t)W * H * 3;
@@ -1279,6 +1312,7 @@ int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const 
 		{
 			a.rgb = s->d_localFrame;
 			a.rgbLocal = 1u;
+			a.rowBulkOk = 0u;
 			a.rgbViewPixels = (size_t)W * H;
 			a.rowWordsOk = ((W * 3u) % 4u == 0 && (frameBytes % 4 == 0 || nv == 1)) ? 1u : 0u;
 		}
