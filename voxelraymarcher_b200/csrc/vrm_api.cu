@@ -346,9 +346,10 @@ int vrm_render_views_device_strided(vrm_scene* s, const float* cameras, uint32_t
 	if (rc) return rc;
 	if (!d_rgb_out || n_views == 0 || n_views > 65535 || view_stride == 0) { s->lastError = "invalid render arguments"; return VRM_ERR_INVALID; }
 	VRM_CUDA(s, cudaSetDevice(s->device));
-	rc = upload_cameras(s, cameras, n_views);
-	if (rc) return rc;
-	return vrm_launch_render(s, s->d_cams, n_views, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out, 0, 0xFFFFFFFFu, view_stride);
+	const bool inlineCam = n_views == 1 && vrm_camera_inline_ok(s);  // the camera of a single view travels in the kernel arguments
+	if (!inlineCam) { rc = upload_cameras(s, cameras, n_views); if (rc) return rc; }
+	return vrm_launch_render(s, inlineCam ? nullptr : s->d_cams, n_views, translation, scale, algorithm, width, height, d_rgb_out, d_hits_out, 0, 0xFFFFFFFFu, view_stride,
+	                         inlineCam ? cameras : nullptr);
 }
 
 int vrm_render_views_device(vrm_scene* s, const float* cameras, uint32_t n_views, const float translation[3], uint32_t scale, int algorithm,
@@ -420,8 +421,8 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 		if (!s->copyStream) VRM_CUDA(s, cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
 		d_rgb = s->d_dmaFrame;
 	}
-	rc = upload_cameras(s, camera, 1);
-	if (rc) return rc;
+	const bool inlineCam = vrm_camera_inline_ok(s);  // the camera travels in the kernel arguments: nothing to upload
+	if (!inlineCam) { rc = upload_cameras(s, camera, 1); if (rc) return rc; }
 	VRM_CUDA(s, cudaEventRecord(s->ev0, s->stream));
 	constexpr int kMaxBands = 8;
 	int bands = 1;
@@ -434,7 +435,7 @@ int vrm_render(vrm_scene* s, const float camera[VRM_CAMERA_FLOATS], const float 
 	{
 		const uint32_t y0 = b ? bandEnd[b - 1] : 0u, y1 = bandEnd[b] < height ? bandEnd[b] : height;
 		if (y1 <= y0) continue;
-		rc = vrm_launch_render(s, s->d_cams, 1, translation, scale, algorithm, width, height, d_rgb, d_hits, y0, y1);
+		rc = vrm_launch_render(s, inlineCam ? nullptr : s->d_cams, 1, translation, scale, algorithm, width, height, d_rgb, d_hits, y0, y1, 1, inlineCam ? camera : nullptr);
 		if (rc) return rc;
 		if (stageRgb || dmaRgb) VRM_CUDA(s, cudaEventRecord(s->evBand[b], s->stream));
 		if (dmaRgb)

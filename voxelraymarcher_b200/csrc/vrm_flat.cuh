@@ -998,10 +998,10 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 #if VRM_FAST_LA
 			// 8: longest-axis stepping (stored-region entry, loop head, a voxel test of the current iteration)
 			const bool isLa = ray.st == kStHead || ray.st == kAdvNone || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
-#if VRM_CLS_LUT && (VRM_FAST_LA & 2)
+#if VRM_CLS_LUT
 			// the class is a function of the state word alone (one nibble per state: kAdvNone 8, kAdvNext 4, kAdvCluster 4, kAdvJump 1,
-			// kAdvRegion 4, kStRegion 4, kStHead 8, the rest 0) except for the null-region entry
-			const unsigned nib = (unsigned)ray.st > 7u ? 0u : ((0x08441448u >> ((unsigned)ray.st * 4u)) & 15u);
+			// kAdvRegion 4, kStRegion 4 (8 when fast_la runs stored-region entries), kStHead 8, the rest 0) except for the null-region entry
+			const unsigned nib = (unsigned)ray.st > 7u ? 0u : ((((VRM_FAST_LA & 2) ? 0x08441448u : 0x08841448u) >> ((unsigned)ray.st * 4u)) & 15u);
 			const unsigned cls = isNull ? 2u : nib;
 			(void)isJump; (void)isLa;
 #else
@@ -1037,29 +1037,34 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 			// The warp stays in a fast block for as long as every marching lane still qualifies (two votes per pass instead of the
 			// classification above): fast_jump leaves a lane in kStMain / kAdvJump, or in kStRegion / kStHead / kStHit; fast_nullskip
 			// leaves it in kStRegion.
-			if (!generic && all == 1u)
+			if (all == 1u || all == 2u)
 			{
-				for (;;)
+				// a lane whose step did not qualify for the fast path it was offered (it changed nothing) sends the warp through the
+				// generic pass below, once
+				bool bad;
+				if (all == 1u)
 				{
-					bool ok = true;
-					if (ray.st == kAdvJump) ok = ray.fast_jump(c);
-					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kAdvJump);
-					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || ray.st == kStRegion || ray.st == kStHead);
-					if (leave != 0u || stay == 0u) { generic = __any_sync(0xFFFFFFFFu, !ok); break; }
+					for (;;)
+					{
+						bool ok = true;
+						if (ray.st == kAdvJump) ok = ray.fast_jump(c);
+						const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kAdvJump);
+						const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || ray.st == kStRegion || ray.st == kStHead);
+						if (leave != 0u || stay == 0u) { bad = __any_sync(0xFFFFFFFFu, !ok); break; }
+					}
 				}
-				continue;
-			}
-			if (!generic && all == 2u)
-			{
-				for (;;)
+				else
 				{
-					bool ok = true;
-					if (ray.st == kStRegion) ok = ray.fast_nullskip(c);
-					const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kStRegion && ray.ri == -1);
-					const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || (ray.st <= kStHead && !(ray.st == kStRegion && ray.ri == -1)));
-					if (leave != 0u || stay == 0u) { generic = __any_sync(0xFFFFFFFFu, !ok); break; }
+					for (;;)
+					{
+						bool ok = true;
+						if (ray.st == kStRegion) ok = ray.fast_nullskip(c);
+						const unsigned stay = __ballot_sync(0xFFFFFFFFu, ok && ray.st == kStRegion && ray.ri == -1);
+						const unsigned leave = __ballot_sync(0xFFFFFFFFu, !ok || (ray.st <= kStHead && !(ray.st == kStRegion && ray.ri == -1)));
+						if (leave != 0u || stay == 0u) { bad = __any_sync(0xFFFFFFFFu, !ok); break; }
+					}
 				}
-				continue;
+				if (!bad) continue;
 			}
 #else
 			if (!generic && all == 1u)

@@ -148,7 +148,10 @@ void vrm_signal_completion(vrm_scene* s, uint32_t frames);
 
 // vrm_render.cu
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
-                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase = 0, uint32_t yEnd = 0xFFFFFFFFu, uint32_t viewStride = 1);
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase = 0, uint32_t yEnd = 0xFFFFFFFFu, uint32_t viewStride = 1, const float* h_cam = nullptr);
+// A single-view launch of the tiled render kernels takes its camera (host pointer h_cam) in the kernel arguments: d_cams may then be null and
+// nothing needs to be uploaded.  The debug forms VRM_RENDER_MODE=0 / 3 read d_cams only.
+inline bool vrm_camera_inline_ok(const vrm_scene* s) { return s->renderMode != 0 && s->renderMode != 3; }
 int vrm_launch_trace(vrm_scene* s, const float* d_rays, uint64_t n, const float* translation, uint32_t scale, int algorithm,
                      uint32_t* d_colour, int32_t* d_hits);
 int vrm_launch_lookup(vrm_scene* s, const int32_t* d_xyz, uint64_t n, uint32_t* d_out, uint8_t* d_exists);

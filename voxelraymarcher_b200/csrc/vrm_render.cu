@@ -62,6 +62,8 @@ struct RenderArgs
 	float translation[3];
 	float scale;
 	const float* cams;  // nViews x 15
+	float cam0[15];     // camInline: the camera of a single-view launch travels in the kernel arguments (constant bank): no upload, no loads
+	uint32_t camInline;
 	uint32_t W, H;
 	size_t viewPixels;     // pixel slots between the outputs of consecutive views (W * H, or a multiple of it for interleaved view sharding)
 	size_t rgbViewPixels;  // the same for the frame array `rgb` alone (it differs when the frames are rendered into the handle's local buffer first)
@@ -259,10 +261,18 @@ __global__ void __launch_bounds__(kRenderThreads, (FORM == 2 && VRM_FUSED_CTAS >
 		float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
 		if (inside)
 		{
-			const float* cam = a.cams + (size_t)blockIdx.z * 15;
 			float camv[15];
+			if (a.camInline)
+			{
 #pragma unroll
-			for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+				for (int i = 0; i < 15; i++) camv[i] = a.cam0[i];
+			}
+			else
+			{
+				const float* cam = a.cams + (size_t)blockIdx.z * 15;
+#pragma unroll
+				for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+			}
 			primary_ray_flat(camv, x, y, a.W, a.H, a.invW, a.invH, o, d);
 			if (a.hits)
 			{
@@ -306,10 +316,18 @@ __global__ void __launch_bounds__(kRenderThreads, (FORM == 2 && VRM_FUSED_CTAS >
 	}
 	else if (inside)
 	{
-		const float* cam = a.cams + (size_t)blockIdx.z * 15;
 		float camv[15];
+		if (a.camInline)
+		{
 #pragma unroll
-		for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+			for (int i = 0; i < 15; i++) camv[i] = a.cam0[i];
+		}
+		else
+		{
+			const float* cam = a.cams + (size_t)blockIdx.z * 15;
+#pragma unroll
+			for (int i = 0; i < 15; i++) camv[i] = __ldg(cam + i);
+		}
 		float o[3], d[3];
 		primary_ray(camv, x, y, a.W, a.H, o, d);
 		hit = march_scene_primary<ST, ALGO, STATS>(c, o, d, a.scale, ss);
@@ -1242,13 +1260,17 @@ template <int ST, int ALGO> void launch_trace_t(vrm_scene* s, TraceArgs a, unsig
 }  // namespace
 
 int vrm_launch_render(vrm_scene* s, const float* d_cams, uint32_t nViews, const float* translation, uint32_t scale, int algorithm,
-                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase, uint32_t yEnd, uint32_t viewStride)
+                      uint32_t W, uint32_t H, uint8_t* d_rgb, int32_t* d_hits, uint32_t yBase, uint32_t yEnd, uint32_t viewStride, const float* h_cam)
 {
 	if (yEnd > H) yEnd = H;
 	vrm_apply_l2_window(s);
 	RenderArgs a;
 	fill_common(a, s, translation, scale);
 	a.cams = d_cams; a.W = W; a.H = H; a.rgb = d_rgb; a.hits = d_hits;
+	a.camInline = 0u;
+	for (int i = 0; i < 15; i++) a.cam0[i] = 0.0f;
+	if (h_cam && nViews == 1 && vrm_camera_inline_ok(s)) { for (int i = 0; i < 15; i++) a.cam0[i] = h_cam[i]; a.camInline = 1u; }
+	else if (!d_cams) { s->lastError = "no camera"; return VRM_ERR_INVALID; }
 	a.invW = 1.0f / (float)W; a.invH = 1.0f / (float)H;
 	a.viewPixels = (size_t)W * H * (viewStride ? viewStride : 1u);
 	a.yBase = yBase; a.yEnd = yEnd;
