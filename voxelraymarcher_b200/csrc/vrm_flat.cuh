@@ -993,33 +993,35 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				}
 			}
 #endif
-			// what the warp's marching lanes (kStMain, kStRegion, kStHead) are about to do: 1 a cluster jump, 2 a null-region skip, 4 anything else
+			// what the warp's marching lanes (kStMain, kStRegion, kStHead) are about to do: a cluster jump, a null-region skip, longest-axis
+			// stepping (loop head, a voxel test of the current iteration; with VRM_FAST_LA & 2 == 0 also a stored-region entry) or anything
+			// else.
+			constexpr unsigned kClsJump = 0x10u, kClsNull = 0x20u, kClsOther = 0x40u, kClsLa = 0x80u;
 			const bool isJump = ray.st == kAdvJump, isNull = ray.st == kStRegion && ray.ri == -1;
 #if VRM_FAST_LA
-			// 8: longest-axis stepping (stored-region entry, loop head, a voxel test of the current iteration)
 			const bool isLa = ray.st == kStHead || ray.st == kAdvNone || ((VRM_FAST_LA & 2) == 0 && ray.st == kStRegion && ray.ri != -1);
 #if VRM_CLS_LUT
-			// the class is a function of the state word alone (one nibble per state: kAdvNone 8, kAdvNext 4, kAdvCluster 4, kAdvJump 1,
-			// kAdvRegion 4, kStRegion 4 (8 when fast_la runs stored-region entries), kStHead 8, the rest 0) except for the null-region entry
-			const unsigned nib = (unsigned)ray.st > 7u ? 0u : ((((VRM_FAST_LA & 2) ? 0x08441448u : 0x08841448u) >> ((unsigned)ray.st * 4u)) & 15u);
-			const unsigned cls = isNull ? 2u : nib;
+			// the class is a function of the state word alone (one nibble per state, already in place: kAdvNone la, kAdvNext other,
+			// kAdvCluster other, kAdvJump jump, kAdvRegion other, kStRegion other (la when fast_la runs stored-region entries), kStHead la,
+			// the rest 0) except for the null-region entry
+			const unsigned nib = (unsigned)ray.st > 7u ? 0u : ((((VRM_FAST_LA & 2) ? 0x84414480u : 0x88414480u) >> ((unsigned)ray.st * 4u)) & 0xF0u);
+			const unsigned cls = isNull ? kClsNull : nib;
 			(void)isJump; (void)isLa;
 #else
-			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : (isLa ? 8u : 4u))) : 0u;
+			const unsigned cls = ray.st <= kStHead ? (isJump ? kClsJump : (isNull ? kClsNull : (isLa ? kClsLa : kClsOther))) : 0u;
 #endif
 #else
-			const unsigned cls = ray.st <= kStHead ? (isJump ? 1u : (isNull ? 2u : 4u)) : 0u;
+			const unsigned cls = ray.st <= kStHead ? (isJump ? kClsJump : (isNull ? kClsNull : kClsOther)) : 0u;
 #endif
 			const unsigned all = __reduce_or_sync(0xFFFFFFFFu, cls);
-			if (all == 0u)
-			{
-				// nobody is marching: every lane is waiting with a hit, done or parked
-				if (!__any_sync(0xFFFFFFFFu, ray.st == kStHit)) break;
-				if (ray.st == kStHit) ray.do_hit(c);
-				continue;
-			}
+			// Four equality tests on one value become a jump table (a constant-bank load + BRX, ~17 times per tile, each a dependent
+			// latency behind the reduction): the jump / null-region tests below read an opaque copy, so the compiler sees two chains of two.
+			unsigned all2 = all;
+#if defined(__CUDA_ARCH__)
+			asm volatile("mov.u32 %0, %1;" : "=r"(all2) : "r"(all));
+#endif
 #if VRM_FAST_LA
-			if (all == 8u)
+			if (all == kClsLa)
 			{
 				for (;;)
 				{
@@ -1033,16 +1035,23 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				continue;
 			}
 #endif
+			if (all == 0u)
+			{
+				// nobody is marching: every lane is waiting with a hit, done or parked
+				if (!__any_sync(0xFFFFFFFFu, ray.st == kStHit)) break;
+				if (ray.st == kStHit) ray.do_hit(c);
+				continue;
+			}
 #if VRM_FAST_LOOPS
 			// The warp stays in a fast block for as long as every marching lane still qualifies (two votes per pass instead of the
 			// classification above): fast_jump leaves a lane in kStMain / kAdvJump, or in kStRegion / kStHead / kStHit; fast_nullskip
 			// leaves it in kStRegion.
-			if (all == 1u || all == 2u)
+			if (all2 == kClsJump || all2 == kClsNull)
 			{
 				// a lane whose step did not qualify for the fast path it was offered (it changed nothing) sends the warp through the
 				// generic pass below, once
 				bool bad;
-				if (all == 1u)
+				if (all2 == kClsJump)
 				{
 					for (;;)
 					{
@@ -1067,14 +1076,14 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 				if (!bad) continue;
 			}
 #else
-			if (!generic && all == 1u)
+			if (!generic && all == kClsJump)
 			{
 				bool ok = true;
 				if (isJump) ok = ray.fast_jump(c);
 				generic = __any_sync(0xFFFFFFFFu, !ok);
 				continue;
 			}
-			if (!generic && all == 2u)
+			if (!generic && all == kClsNull)
 			{
 				bool ok = true;
 				if (isNull) ok = ray.fast_nullskip(c);
