@@ -1004,7 +1004,8 @@ VRM_HD uint32_t march_scene_flat_warp(RayCtx<ST, STATS>& c, bool active, const f
 			// the class is a function of the state word alone (one nibble per state, already in place: kAdvNone la, kAdvNext other,
 			// kAdvCluster other, kAdvJump jump, kAdvRegion other, kStRegion other (la when fast_la runs stored-region entries), kStHead la,
 			// the rest 0) except for the null-region entry
-			const unsigned nib = (unsigned)ray.st > 7u ? 0u : ((((VRM_FAST_LA & 2) ? 0x84414480u : 0x88414480u) >> ((unsigned)ray.st * 4u)) & 0xF0u);
+			// (a clamped funnel shift: states 8 and 9 shift the table out completely)
+			const unsigned nib = __funnelshift_rc((VRM_FAST_LA & 2) ? 0x84414480u : 0x88414480u, 0u, (unsigned)ray.st * 4u) & 0xF0u;
 			const unsigned cls = isNull ? kClsNull : nib;
 			(void)isJump; (void)isLa;
 #else
