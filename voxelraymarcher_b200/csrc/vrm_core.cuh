@@ -301,6 +301,9 @@ VRM_HD uint32_t hash_slot2(uint32_t key, uint32_t seed, uint32_t n) { return mul
 #ifndef VRM_COORD64_EMPTY
 #define VRM_COORD64_EMPTY 1
 #endif
+#ifndef VRM_HASH_INCR_KEY
+#define VRM_HASH_INCR_KEY 1  // nested longest-axis walk over the hash table: the lookup key is kept up to date by the test loop (march_longest_axis)
+#endif
 #ifndef VRM_HASH_CLUSTER_FILTER
 #define VRM_HASH_CLUSTER_FILTER 1
 #endif
@@ -427,28 +430,50 @@ VRM_HD bool space_exists(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& 
 // g0..g2 are region-local coordinates in walk order; reg[] the region in walk order (for the hit record).
 // The nested traversal records the pixel's first stored voxel here, in c.hit; the state machine of
 // vrm_flat.cuh has its own fused test site and records at the hit site instead.
+// The cuckoo lookup on a ready-made key (lookup_voxel below; the nested longest-axis walk keeps the key up to date itself).
+template <bool STATS>
+VRM_HD uint32_t lookup_hash_key(RayCtx<kStorageHash, STATS>& c, const RegionRef<kStorageHash>& rh, uint32_t key)
+{
+	uint32_t v = kEmpty;
+#if VRM_HASH_CLUSTER_FILTER
+	// negative filter: a voxel whose 8^3 cluster holds no voxel at all cannot be in the table, and the 64-byte mask of the
+	// region answers that from L1 -- most lookups of a walk through open space never touch the (much larger) slot arrays.
+	// The traversal is untouched (the hash table's doesVoxelSpaceExist stays true: no cluster is ever skipped).
+	if (hash_cluster_occupied(c.sv.clusterMask, rh.ri, key))
+#endif
+	{
+		// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
+		unsigned long long e1 = ldg(c.sv.slots + (rh.base1 + hash_slot1(key, rh.seed1, rh.n)));
+		unsigned long long e2 = ldg(c.sv.slots + (rh.base2 + hash_slot2(key, rh.seed2, rh.n)));
+		if ((uint32_t)(e1 >> 32) == key) v = (uint32_t)e1;
+		else if ((uint32_t)(e2 >> 32) == key) v = (uint32_t)e2;
+	}
+	if (STATS) c.st.nProbe2++;
+	return v;
+}
+
+// A lookup found a stored voxel: the pixel's first one is its hit (see RayCtx::hit)
+template <int ST, bool STATS, class P>
+VRM_HD void note_lookup_hit(RayCtx<ST, STATS>& c, const P& p, const int* reg, int g0, int g1, int g2)
+{
+	if (STATS) c.st.nLookupHit++;
+	if (!c.hit[3])
+	{
+		int gw[3] = {reg[0] * kRegion + g0, reg[1] * kRegion + g1, reg[2] * kRegion + g2};
+		int gx[3];
+		to_world(p, gw, gx);
+		c.hit[0] = gx[0]; c.hit[1] = gx[1]; c.hit[2] = gx[2]; c.hit[3] = 1;
+	}
+}
+
 template <int ST, bool STATS, class P>
 VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const P& p, const int* reg, int g0, int g1, int g2)
 {
 	uint32_t v = kEmpty;
 	if constexpr (ST == kStorageHash)
 	{
-		const RegionRef<kStorageHash>& rh = r;
-		uint32_t key = ((uint32_t)g0 << p.ks(0)) | ((uint32_t)g1 << p.ks(1)) | ((uint32_t)g2 << p.ks(2));
-#if VRM_HASH_CLUSTER_FILTER
-		// negative filter: a voxel whose 8^3 cluster holds no voxel at all cannot be in the table, and the 64-byte mask of the
-		// region answers that from L1 -- most lookups of a walk through open space never touch the (much larger) slot arrays.
-		// The traversal is untouched (the hash table's doesVoxelSpaceExist stays true: no cluster is ever skipped).
-		if (hash_cluster_occupied(c.sv.clusterMask, rh.ri, key))
-#endif
-		{
-			// both probes are issued before either compare: a miss (the common case) costs one round trip, not two
-			unsigned long long e1 = ldg(c.sv.slots + (rh.base1 + hash_slot1(key, rh.seed1, rh.n)));
-			unsigned long long e2 = ldg(c.sv.slots + (rh.base2 + hash_slot2(key, rh.seed2, rh.n)));
-			if ((uint32_t)(e1 >> 32) == key) v = (uint32_t)e1;
-			else if ((uint32_t)(e2 >> 32) == key) v = (uint32_t)e2;
-		}
-		if (STATS) c.st.nProbe2++;
+		const uint32_t key = ((uint32_t)g0 << p.ks(0)) | ((uint32_t)g1 << p.ks(1)) | ((uint32_t)g2 << p.ks(2));
+		v = lookup_hash_key(c, r, key);
 	}
 	else
 	{
@@ -466,17 +491,7 @@ VRM_HD uint32_t lookup_voxel(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const
 		}
 	}
 	if (STATS) c.st.nLookup++;
-	if (v != kEmpty)
-	{
-		if (STATS) c.st.nLookupHit++;
-		if (!c.hit[3])
-		{
-			int gw[3] = {reg[0] * kRegion + g0, reg[1] * kRegion + g1, reg[2] * kRegion + g2};
-			int gx[3];
-			to_world(p, gw, gx);
-			c.hit[0] = gx[0]; c.hit[1] = gx[1]; c.hit[2] = gx[2]; c.hit[3] = 1;
-		}
-	}
+	if (v != kEmpty) note_lookup_hit(c, p, reg, g0, g1, g2);
 	return v;
 }
 
@@ -932,6 +947,23 @@ VRM_HD uint32_t voxel_space_jump(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, c
 // "bump one axis, test the voxel space, look the voxel up" unit.  Here the sub-case only selects the ORDER of
 // slots to test (packed 2 bits each into `seq`); one shared test site then runs 1-3 times.  Same tests in the same
 // order, but lanes of a warp that are in different sub-cases execute the same instructions instead of serialising.
+// a voxel test of the longest-axis walk found a voxel: where, and which face (Renderer.cuh:818-822, 899, 753-758)
+VRM_HD void la_test_hit(const PermRuntime& p, const LaState& s, int slot, HitInfo& h)
+{
+	float odS = pick3(slot, s.od[0], s.od[1], s.od[2]);
+	h.nAxisW = p.axis(slot);
+	h.nSign = copysignf(1.0f, -odS);
+	if (slot == 0) { h.pos[0] = s.ro[0]; h.pos[1] = s.ro[1]; h.pos[2] = s.ro[2]; }  // Renderer.cuh:899
+	else
+	{
+		// getLocalHitLocation, Renderer.cuh:753-758
+		float ooS = pick3(slot, s.oo[0], s.oo[1], s.oo[2]);
+		float tl = odS > 0.0f ? vdiv(vsub(ceilf(ooS), ooS), odS) : vdiv(vsub(floorf(ooS), ooS), odS);
+		h.pos[0] = along(s.oo[0], tl, s.od[0]); h.pos[1] = along(s.oo[1], tl, s.od[1]); h.pos[2] = along(s.oo[2], tl, s.od[2]);
+	}
+	h.laShadow = 1;
+}
+
 template <int ST, bool STATS, bool SHADOW>
 VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r, const PermRuntime& p, float* o, const RayDir& k, const RayDir& ko, const int* reg, HitInfo& h)
 {
@@ -948,6 +980,15 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 	s.ad[1] = (int)s.ro[1] - s.g[1];
 	s.ad[2] = (int)s.ro[2] - s.g[2];
 	const bool roundDown = s.od[1] < 0.0f;  // Renderer.cuh:784
+	// Hash table (VRM_HASH_INCR_KEY): every voxel of the walk is looked up (doesVoxelSpaceExist is always true, nothing is skipped),
+	// so the test loop keeps the lookup KEY up to date -- one add of the tested slot's step, ad << ks -- instead of bumping three grid
+	// values and packing them again for every test; the grid values are unpacked from the key once per iteration (and at a hit).
+	// Fields are 7 bits wide and the grid values stay in [0, 64], so sums and ORs of the fields agree.
+	constexpr bool kIncrKey = VRM_HASH_INCR_KEY && ST == kStorageHash;
+	uint32_t key = 0u, kst1 = 0u, kst2 = 0u;
+	const int ks0 = p.ks(0), ks1 = p.ks(1), ks2 = p.ks(2);
+	const uint32_t kst0 = (uint32_t)s.ad[0] << ks0;
+	if constexpr (kIncrKey) key = ((uint32_t)s.g[0] << ks0) | ((uint32_t)s.g[1] << ks1) | ((uint32_t)s.g[2] << ks2);
 
 	while (grid_in_region(s.g[0] + s.ad[0], s.g[1] + s.ad[1], s.g[2] + s.ad[2]))
 	{
@@ -967,6 +1008,28 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 		else if (s.ad[2] != 0) { seq = 2u; nTests = 2; }  // Renderer.cuh:865
 		else { seq = 0u; nTests = 1; }
 		bool again = false;
+		if constexpr (kIncrKey)
+		{
+			kst1 = (uint32_t)s.ad[1] << ks1; kst2 = (uint32_t)s.ad[2] << ks2;
+			for (int i = 0; i < nTests; i++)
+			{
+				const int slot = (int)(seq & 3u);
+				seq >>= 2;
+				key += slot == 0 ? kst0 : (slot == 1 ? kst1 : kst2);
+				if (STATS) c.st.nExist++;  // space_exists: always true for the hash table
+				const uint32_t col = lookup_hash_key(c, r, key);
+				if (STATS) c.st.nLookup++;
+				if (col != kEmpty)
+				{
+					s.g[0] = (int)((key >> ks0) & 127u); s.g[1] = (int)((key >> ks1) & 127u); s.g[2] = (int)((key >> ks2) & 127u);
+					note_lookup_hit(c, p, reg, s.g[0], s.g[1], s.g[2]);
+					if (!SHADOW) la_test_hit(p, s, slot, h);
+					return col;
+				}
+			}
+			s.g[0] = (int)((key >> ks0) & 127u); s.g[1] = (int)((key >> ks1) & 127u); s.g[2] = (int)((key >> ks2) & 127u);
+		}
+		else
 		for (int i = 0; i < nTests; i++)
 		{
 			int slot = (int)(seq & 3u);
@@ -984,21 +1047,7 @@ VRM_HD uint32_t march_longest_axis(RayCtx<ST, STATS>& c, const RegionRef<ST>& r,
 			uint32_t col = lookup_voxel(c, r, p, reg, s.g[0], s.g[1], s.g[2]);
 			if (col != kEmpty)
 			{
-				if (!SHADOW)
-				{
-					float odS = pick3(slot, s.od[0], s.od[1], s.od[2]);
-					h.nAxisW = p.axis(slot);
-					h.nSign = copysignf(1.0f, -odS);
-					if (slot == 0) { h.pos[0] = s.ro[0]; h.pos[1] = s.ro[1]; h.pos[2] = s.ro[2]; }  // Renderer.cuh:899
-					else
-					{
-						// getLocalHitLocation, Renderer.cuh:753-758
-						float ooS = pick3(slot, s.oo[0], s.oo[1], s.oo[2]);
-						float tl = odS > 0.0f ? vdiv(vsub(ceilf(ooS), ooS), odS) : vdiv(vsub(floorf(ooS), ooS), odS);
-						h.pos[0] = along(s.oo[0], tl, s.od[0]); h.pos[1] = along(s.oo[1], tl, s.od[1]); h.pos[2] = along(s.oo[2], tl, s.od[2]);
-					}
-							h.laShadow = 1;
-				}
+				if (!SHADOW) la_test_hit(p, s, slot, h);
 				return col;
 			}
 		}
