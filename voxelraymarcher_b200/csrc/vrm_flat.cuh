@@ -20,7 +20,8 @@
 // permutation is three storage shifts + three region-table strides, state and advance mode are ONE word, flags are bits of another,
 // the tX/tY/tZ/tMin of the last advance are reduced to the three equality bits the normal needs, and the light's direction constants
 // come precomputed from the host (LightWalk).  The fused render kernel is compiled for 56 registers (9 CTAs per SM): ptxas then spills
-// ~0.5 KB per thread, 2.9 % of the executed instructions -- measured faster than 64 registers without spills.
+// ~0.5 KB per thread, 3 % of the executed instructions, all of it in the generic pass -- measured faster than 64 registers with a
+// quarter of the spills (1.224 vs 1.244 ms).
 //
 // ARITHMETIC IS UNCHANGED: the same operations in the same order as vrm_core.cuh / the reference -- only the order in
 // which different rays' operations are interleaved changes.  tests/hostsim runs this very code on the CPU against the
