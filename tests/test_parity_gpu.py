@@ -283,6 +283,33 @@ def test_pinned_host_buffer_is_written_directly(probe):
         assert got["rgb"] is not None and want["hits"][..., 3].sum() > 0
 
 
+@pytest.mark.parametrize("storage,algo", COMBOS)
+def test_remote_frame_rows_as_bulk_copies_equal_plain_stores(probe, storage, algo, monkeypatch):
+    """A frame outside the GPU's own memory (here: page-locked host memory) leaves the CTA as bulk async copies (cp.async.bulk) when every
+    96-byte row segment is 16-byte aligned, else as ordinary stores: both forms, at an aligned width, at a width whose rows are only
+    4-byte aligned (W * 3 % 16 != 0) and through a frame base that is only 4-byte aligned, must equal the device-frame render."""
+    import torch
+    xyz, rgb = probe
+    frames = {}
+    for bulk in ("1", "0"):
+        monkeypatch.setenv("VRM_BULK_STORE", bulk)   # read at vrm_scene_create
+        s = build_product(xyz, rgb, storage)
+        for (w, h, off) in ((640, 360, 0), (644, 360, 0), (640, 360, 4)):
+            cam = api.Camera((14.0, 9.0, 12.0), (4.0, 3.0, 2.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h))
+            dev = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda:0")
+            s.render_device(w, h, algo, cam, dev.data_ptr(), scale=8)
+            s.synchronize()
+            pinned = torch.zeros(h * w * 3 + 16, dtype=torch.uint8).pin_memory()
+            view = pinned.numpy()[off:off + h * w * 3].reshape(h, w, 3)
+            s.render(w, h, algo, cam, scale=8, rgb_out=view)
+            assert np.array_equal(view, dev.cpu().numpy()), (bulk, w, h, off)
+            assert view.any()
+            frames[(bulk, w, off)] = view.copy()
+        s.close()
+    for (bulk, w, off), f in frames.items():
+        assert np.array_equal(f, frames[("1", w, off)])
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("algo", ["original", "longestaxis"])
 def test_crawl_fast_forward_is_bit_exact(algo):
