@@ -19,7 +19,7 @@ ranks do not wait for each other between steps; rank 0's last step ends when eve
 
 value  = W*H*N*K / t, t = max over ranks of the summed per-step CUDA-event time; inputs and outputs resident in HBM.  L2 is
          flushed between steps (outside the per-step event pairs).
-e2e    = the same metric through the host-buffer C-ABI call vrm_render (camera H2D + frame D2H inside the timed region).
+e2e    = the same metric through the host-buffer C-ABI call vrm_render (camera host -> device in the kernel arguments + frame D2H inside the timed region).
 """
 from __future__ import annotations
 
@@ -395,7 +395,7 @@ def main():
             del full
         dist.barrier()
 
-    # ---- e2e: host-buffer C-ABI call (camera H2D + frame D2H inside the timed region), pinned result buffer ---------
+    # ---- e2e: host-buffer C-ABI call (camera host -> device + frame D2H inside the timed region), pinned result buffer ---------
     host_frame = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.uint8).pin_memory()
     host_np = host_frame.numpy()
     e2e_s = 0.0
