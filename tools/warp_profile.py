@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--view", type=int, default=0)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--regroup", default="", help="budget:maxLanes[,budget:maxLanes...]: simulate abandon + re-trace of long-tailed tiles (sim_regroup_profile)")
+    ap.add_argument("--compact", default="", help="tiles per CTA, e.g. 2,4,8: simulate packing the shadow rays of a CTA's tiles into full warps (sim_cta_compact_profile)")
     ap.add_argument("--scene", default="terrain", choices=["terrain", "shells2048"], help="shells2048: BASELINE configs[3], one 1080p view of its orbit")
     a = ap.parse_args()
     lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
@@ -49,6 +50,17 @@ def main():
         cam = bench.orbit_views_2048(api, W, H)[a.view]
     camv = np.ascontiguousarray(cam.data, np.float32)
     tr = np.zeros(3, np.float32)
+    if a.compact:
+        for tpc in (int(v) for v in a.compact.split(",")):
+            out = np.zeros(7, np.uint64)
+            rc = lib.sim_cta_compact_profile(h, camv.ctypes.data_as(ctypes.c_void_p), tr.ctypes.data_as(ctypes.c_void_p), 1, W, H, a.stride, tpc,
+                                             out.ctypes.data_as(ctypes.c_void_p), a.threads)
+            assert rc == 0
+            ctas, pp, sp, spk, slp, srays, worst = (int(v) for v in out)
+            tiles = ctas * tpc
+            print(f"tiles/CTA {tpc}: primary passes/tile {pp / tiles:.2f}, shadow passes/tile {sp / tiles:.2f} (lanes/pass {slp / max(sp, 1):.1f}) -> packed {spk / tiles:.2f}; "
+                  f"all passes {100 * (pp + spk) / (pp + sp):.1f} %; shadow rays/tile {srays / tiles:.2f}; worst tile of a CTA / mean primary passes {worst * tpc / pp:.2f}")
+        return
     if a.regroup:
         for spec in a.regroup.split(","):
             budget, lanes_max = (int(v) for v in spec.split(":"))
