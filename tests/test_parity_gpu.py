@@ -283,6 +283,27 @@ def test_pinned_host_buffer_is_written_directly(probe):
         assert got["rgb"] is not None and want["hits"][..., 3].sum() > 0
 
 
+@pytest.mark.parametrize("w,h", [(250, 141), (33, 5), (7, 3), (1, 1), (644, 362)])
+def test_device_frames_at_ragged_resolutions_equal_host_frames(probe, w, h):
+    """The fused kernel has two store forms with their own pixel-to-thread layout -- per-warp stores for a frame in the GPU's own memory,
+    CTA-staged rows for a frame elsewhere (here: the handle's page-locked staging frame behind a pageable buffer).  Both must give the
+    same frame at sizes that are no multiple of a tile or a CTA, for a single view and for a 3-view batch."""
+    import torch
+    xyz, rgb = probe
+    s = build_product(xyz, rgb, "vcs")
+    cams = [api.Camera((14.0 - 2.0 * v, 9.0, 12.0 + v), (4.0, 3.0, 2.0), (0.0, 1.0, 0.0), 60.0, np.float32(w) / np.float32(h)) for v in range(3)]
+    want = [s.render(w, h, "longestaxis", c, scale=8)["rgb"] for c in cams]
+    one = torch.full((h, w, 3), 7, dtype=torch.uint8, device="cuda:0")
+    s.render_device(w, h, "longestaxis", cams[0], one.data_ptr(), scale=8)
+    batch = torch.full((3, h, w, 3), 7, dtype=torch.uint8, device="cuda:0")
+    s.render_views_device(w, h, "longestaxis", cams, batch.data_ptr(), scale=8)
+    s.synchronize()
+    assert np.array_equal(one.cpu().numpy(), want[0])
+    for v in range(3):
+        assert np.array_equal(batch[v].cpu().numpy(), want[v]), v
+    s.close()
+
+
 @pytest.mark.parametrize("storage,algo", COMBOS)
 def test_remote_frame_rows_as_bulk_copies_equal_plain_stores(probe, storage, algo, monkeypatch):
     """A frame outside the GPU's own memory (here: page-locked host memory) leaves the CTA as bulk async copies (cp.async.bulk) when every
